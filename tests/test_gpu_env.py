@@ -1,0 +1,226 @@
+"""Parity of the fused env step (reset / step / obs / state / reward / info) with the oracle's
+restatement of reference voltage_control_env.py. Reward tolerance of BASELINE.json: 1e-5; held to 1e-9."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, random_tree_net
+from mapdn_b200 import cases
+from mapdn_b200.network import ProfileDesc
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(ROOT, "tests", "golden")
+TOL = 1e-9
+
+
+def _make(net, prof, args, batch, **kw):
+    from mapdn_b200.env import BatchedVoltageControl
+    return BatchedVoltageControl(net, prof, args, batch=batch, **kw)
+
+
+def _cmp_step(env, oracles, ids, a, add_noise=True):
+    from oracle.voltage_control_ref import INFO_KEYS
+    r, term, info = env.step(torch.tensor(a, device=env.device), add_noise=add_noise)
+    st = env.get_state()
+    obs2 = env.obs.clone()
+    obs3 = env.get_obs().clone()                     # standalone get_obs kernel == fused output
+    torch.cuda.synchronize()
+    assert torch.equal(obs2, obs3)
+    for o, i in zip(oracles, ids):
+        ro, to, io = o.step(a[i], add_noise=add_noise)
+        assert abs(ro - r[i].item()) < TOL
+        assert to == bool(term[i].item())
+        for j, k in enumerate(INFO_KEYS):
+            assert abs(io[k] - info[i, j].item()) < TOL, k
+        assert np.abs(np.array(o.get_obs()) - obs2[i].cpu().numpy()).max() < TOL
+        assert np.abs(o.get_state() - st[i].cpu().numpy()).max() < 1e-8
+
+
+def test_golden_trajectory_case33():
+    from oracle.voltage_control_ref import INFO_KEYS
+    g = np.load(os.path.join(GOLD, "traj_case33.npz"))
+    net, prof = cases.make_case("case33"), cases.make_profiles("case33", n_days=4)
+    env = _make(net, prof, dict(voltage_barrier_type="bowl", action_scale=0.8, seed=11), batch=6)
+    obs, state = env.reset()
+    ids = g["env_ids"]
+    torch.cuda.synchronize()
+    assert env.get_field("start_row")[ids, 0].cpu().tolist() == g["start"].tolist()
+    assert np.abs(obs[ids].cpu().numpy() - g["obs0"]).max() < TOL
+    assert np.abs(state[ids].cpu().numpy() - g["state0"]).max() < 1e-8
+    for t in range(6):
+        a = np.zeros((6, net.n_sgen)); a[ids] = g["actions"][t]
+        r, term, info = env.step(torch.tensor(a, device=env.device))
+        torch.cuda.synchronize()
+        assert np.abs(r[ids].cpu().numpy() - g["reward"][:, t]).max() < TOL
+        assert np.abs(info[ids].cpu().numpy() - g["info"][:, t]).max() < TOL
+        assert np.abs(env.obs[ids].cpu().numpy() - g["obs"][:, t]).max() < TOL
+        assert np.abs(env.get_state()[ids].cpu().numpy() - g["state"][:, t]).max() < 1e-8
+    assert len(INFO_KEYS) == info.shape[1]
+
+
+@pytest.mark.parametrize("name,barrier,lanes", [("case33", "bowl", 0), ("case33", "bump", 32), ("case33", "l2", 4),
+                                                 ("case141", "l1", 0), ("case322", "courant_beltrami", 0)])
+@pytest.mark.parametrize("add_noise", [True, False])
+def test_trajectory_matches_oracle(name, barrier, lanes, add_noise):
+    from oracle.voltage_control_ref import VoltageControlOracle
+    net, prof = cases.make_case(name), cases.make_profiles(name, n_days=4)
+    args = dict(voltage_barrier_type=barrier, action_scale=cases.SCENARIOS[name]["action_scale"], seed=5)
+    B = 21
+    env = _make(net, prof, args, batch=B, lanes_per_env=lanes, env_id_offset=1000)
+    ids = [0, 7, B - 1]
+    oracles = [VoltageControlOracle(net, prof, env.args, env_id=1000 + i) for i in ids]
+    if add_noise:
+        obs, state = env.reset()
+        for o, i in zip(oracles, ids):
+            oo, os_ = o.reset()
+            assert np.abs(np.array(oo) - obs[i].cpu().numpy()).max() < TOL
+            assert np.abs(os_ - state[i].cpu().numpy()).max() < 1e-8
+    else:
+        start = torch.tensor([[i % 3, (5 * i) % 24, i % 20] for i in range(B)], dtype=torch.int32, device=env.device)
+        obs, state = env.reset(start, add_noise=False)
+        for o, i in zip(oracles, ids):
+            oo, os_ = o.reset(start=tuple(start[i].tolist()), add_noise=False)
+            assert np.abs(np.array(oo) - obs[i].cpu().numpy()).max() < TOL
+    rng = np.random.default_rng(3)
+    for t in range(5):
+        a = rng.uniform(env.action_space.low, env.action_space.high, (B, env.n_agents))
+        _cmp_step(env, oracles, ids, a, add_noise)
+    # second episode: the episode counter re-keys the RNG
+    env.reset()
+    for o in oracles:
+        o.reset()
+    a = rng.uniform(env.action_space.low, env.action_space.high, (B, env.n_agents))
+    _cmp_step(env, oracles, ids, a, True)
+
+
+def test_line_weight_reward_and_general_net():
+    """line_weight branch of the reward (reference :612-613) on a net with transformers (res_line excludes
+    them), shunts, scaling factors and a non-zero slack angle."""
+    from oracle.voltage_control_ref import VoltageControlOracle
+    net = random_tree_net(23, 4, seed=11)
+    rng = np.random.default_rng(2)
+    T = 3 * 480 + 1
+    prof = ProfileDesc(pv=rng.uniform(0.1, 0.5, (T, net.n_sgen)), load_p=rng.uniform(0.0, 0.3, (T, net.n_load)),
+                       load_q=rng.uniform(0.0, 0.1, (T, net.n_load)), steps_per_hour=20, n_days=3)
+    args = dict(voltage_barrier_type="l1", line_weight=0.7, q_weight=None, action_scale=0.5, action_bias=0.1, seed=9)
+    env = _make(net, prof, args, batch=5)
+    oracles = [VoltageControlOracle(net, prof, env.args, env_id=i) for i in range(5)]
+    obs, _ = env.reset()
+    for o, i in zip(oracles, range(5)):
+        assert np.abs(np.array(o.reset()[0]) - obs[i].cpu().numpy()).max() < TOL
+    for t in range(4):
+        a = rng.uniform(-0.4, 0.6, (5, net.n_sgen))
+        _cmp_step(env, oracles, range(5), a)
+
+
+def test_divergence_branch_matches_reference_semantics():
+    """reference :188-196,204 - reward from the previous net - 200, destroy=1, q_loss=attempted, terminate,
+    state rolled back; SURVEY Appendix B.6."""
+    from oracle.voltage_control_ref import VoltageControlOracle
+    net = cases.case33()
+    prof = cases.make_profiles("case33", n_days=4)
+    # a profile whose rows >= 60 carry a demand the feeder cannot serve
+    lp = prof.load_p.copy(); lp[60:] *= 60.0
+    prof = ProfileDesc(pv=prof.pv, load_p=lp, load_q=prof.load_q, steps_per_hour=20, n_days=prof.n_days)
+    args = dict(voltage_barrier_type="l1", seed=1)
+    B = 9
+    env = _make(net, prof, args, batch=B, lanes_per_env=8)
+    start = torch.tensor([[0, 2, 15 + (i % 4)] for i in range(B)], dtype=torch.int32, device=env.device)  # rows 55..58
+    env.reset(start, add_noise=False)
+    oracles = [VoltageControlOracle(net, prof, env.args, env_id=i) for i in range(B)]
+    for o, i in zip(oracles, range(B)):
+        o.reset(start=tuple(start[i].tolist()), add_noise=False)
+    rng = np.random.default_rng(0)
+    seen_fail = False
+    for t in range(7):
+        a = rng.uniform(-0.8, 0.8, (B, 6))
+        alive = [i for i in range(B) if not getattr(oracles[i], "dead", False)]
+        r, term, info = env.step(torch.tensor(a, device=env.device), add_noise=False)
+        torch.cuda.synchronize()
+        for i in alive:
+            ro, to, io = oracles[i].step(a[i], add_noise=False)
+            assert abs(ro - r[i].item()) < 1e-8 and to == bool(term[i].item())
+            assert io["destroy"] == info[i, 10].item()
+            assert abs(io["q_loss"] - info[i, 9].item()) < TOL and io["totally_controllable_ratio"] == info[i, 3].item()
+            assert np.abs(np.array(oracles[i].get_obs()) - env.obs[i].cpu().numpy()).max() < TOL
+            if io["destroy"] == 1.0:
+                seen_fail = True
+                oracles[i].dead = True
+                assert ro < -200.0
+    assert seen_fail
+
+
+def test_masked_reset_and_episode_termination():
+    net, prof = cases.make_case("case33"), cases.make_profiles("case33", n_days=4)
+    env = _make(net, prof, dict(episode_limit=5, seed=2), batch=8)
+    env.reset()
+    a = torch.zeros(8, 6, dtype=torch.float64, device=env.device)
+    terms = []
+    for _ in range(4):
+        _, term, _ = env.step(a)
+        terms.append(term.clone())
+    torch.cuda.synchronize()
+    assert [int(t.sum()) for t in terms] == [0, 0, 0, 8]              # steps 2,3,4,5 -> 5 >= episode_limit
+    assert env.get_field("steps")[:, 0].cpu().tolist() == [5.0] * 8
+    before = env.get_field("start_row").clone()
+    mask = torch.tensor([1, 0, 1, 0, 0, 0, 0, 1], dtype=torch.uint8, device=env.device)
+    env.reset(mask=mask)
+    torch.cuda.synchronize()
+    steps = env.get_field("steps")[:, 0].cpu().numpy()
+    assert steps.tolist() == [1, 5, 1, 5, 5, 5, 5, 1]
+    assert torch.equal(env.get_field("start_row")[mask == 0], before[mask == 0])
+    assert env.get_field("sum_rewards")[0, 0].item() == 0.0 and env.get_field("sum_rewards")[1, 0].item() != 0.0
+
+
+def test_step_host_equals_device_path():
+    net, prof = cases.make_case("case33"), cases.make_profiles("case33", n_days=4)
+    e1 = _make(net, prof, dict(seed=4, voltage_barrier_type="bowl"), batch=32)
+    e2 = _make(net, prof, dict(seed=4, voltage_barrier_type="bowl"), batch=32)
+    e1.reset(); e2.reset()
+    rng = np.random.default_rng(0)
+    for _ in range(3):
+        a = rng.uniform(-0.8, 0.8, (32, 6))
+        r1, t1, i1 = e1.step(torch.tensor(a, device=e1.device))
+        r2, t2, i2, o2 = e2.step_host(a)
+        torch.cuda.synchronize()
+        assert np.array_equal(r1.cpu().numpy(), r2) and np.array_equal(t1.cpu().numpy(), t2)
+        assert np.array_equal(i1.cpu().numpy(), i2) and np.array_equal(e1.obs.cpu().numpy(), o2)
+
+
+def test_voltage_control_shim_api():
+    """The reference call pattern (code_examples.py:34-58, models/model.py:204-221, utilities/tester.py:34-56)."""
+    from mapdn_b200.env import VoltageControl
+    from oracle.voltage_control_ref import INFO_KEYS, VoltageControlOracle
+    env = VoltageControl(dict(scenario="case33", voltage_barrier_type="bowl", action_scale=0.8, action_bias=0.0,
+                              mode="distributed", episode_limit=240, seed=0, data_path="unused"))
+    assert env.get_num_of_agents() == 6 and env.get_total_actions() == 1
+    assert env.get_obs_size() == 50 and env.get_state_size() == 144
+    info = env.get_env_info()
+    assert info == dict(state_shape=144, obs_shape=50, n_actions=1, n_agents=6, episode_limit=240)
+    obs, state = env.manual_reset(1, 23, 2)
+    assert len(obs) == 6 and obs[0].shape == (50,) and state.shape == (144,)
+    net, prof = cases.make_case("case33"), cases.make_profiles("case33")
+    o = VoltageControlOracle(net, prof, dict(voltage_barrier_type="bowl", action_scale=0.8, seed=0))
+    o.reset()                                   # the constructor's reset() is episode 1 (reference :85)
+    oo, os_ = o.reset(start=(1, 23, 2), add_noise=False)
+    assert np.abs(np.array(oo) - np.array(obs)).max() < TOL and np.abs(os_ - state).max() < 1e-8
+    assert env.get_avail_actions().shape == (1, 6, 1)
+    for t in range(3):
+        a = env.get_action()
+        assert a.shape == (6,) and a.min() >= -0.8 and a.max() <= 0.8
+        reward, done, info = env.step(a, add_noise=False)
+        ro, to, io = o.step(a, add_noise=False)
+        assert isinstance(reward, float) and isinstance(done, bool) and set(info) == set(INFO_KEYS)
+        assert abs(reward - ro) < TOL and done == to
+        assert np.abs(np.array(env.get_obs()) - np.array(o.get_obs())).max() < TOL
+        assert np.abs(env._get_res_bus_v() - o.g.res.vm_pu).max() < TOL
+        assert np.abs(env._get_sgen_active() - o.g.sgen_p).max() < 1e-12
+        assert np.abs(env._get_sgen_reactive() - o.g.sgen_q).max() < 1e-12
+        assert np.abs(env._get_res_line_loss() - o.g.res.pl_mw).max() < TOL
+        assert np.abs(env._get_res_bus_active() - o.g.res.p_mw).max() < 1e-8
+    assert env.steps == 4
+    obs, state = env.reset()
+    assert env.steps == 1 and env.sum_rewards == 0
+    env.close()
