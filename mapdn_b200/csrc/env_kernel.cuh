@@ -3,9 +3,13 @@
 // next profile row (+ noise) -> zone-masked observation gather. One launch per env step.
 //
 // Work decomposition: G lanes of a warp own one env instance (32/G envs per warp); the env's
-// Newton state lives in shared memory (22 doubles per bus); the network's admittances and the
-// elimination schedule (identical for all envs) are staged once per CTA with a TMA bulk copy.
-// The Newton loop never touches HBM.
+// Newton state lives in shared memory (9 double2 per PQ bus, 128-bit accesses); the network's
+// admittances, the elimination schedule, the element->bus maps and the observation program
+// (identical for all envs) are staged once per CTA with a TMA bulk copy. The Newton loop never
+// touches HBM and is written branch-light: every "missing child" points at an all-zero slot.
+//
+// The linear solve works on the forest of PQ buses (the slack bus is not an unknown), each tree
+// re-rooted at its centre so that the leaf->root elimination has half the depth of the feeder.
 //
 // Replaces, per env: reference voltage_control_env.py step :178-211, _take_action :548-566,
 // _clip_reactive_power :568-572, pp.runpp (pandapower 2.7.0 newtonpf),
@@ -22,6 +26,7 @@ namespace mapdn {
 enum Mode { MODE_SOLVE = 0, MODE_STEP = 1, MODE_RESET = 2 };
 constexpr int kMaxResetAttempts = 16;
 constexpr unsigned kFull = 0xffffffffu;
+constexpr double kRad2Deg = 57.295779513082320876798;
 
 __device__ __forceinline__ double nanmax(double a, double b) { return (b > a || b != b) ? b : a; }
 
@@ -39,6 +44,20 @@ template <int G> __device__ __forceinline__ double group_max(double v) {
 #pragma unroll
   for (int m = G / 2; m >= 1; m >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, m));
   return v;
+}
+
+// Reciprocal without the library's special-case branch: MUFU.RCP64H seed + two Newton steps
+// (|rel err| ~ 1 ulp). A zero / denormal pivot yields inf/NaN, which the solver reports as
+// "not converged" - the same outcome pandapower reaches through a singular-matrix warning.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
 }
 
 // ---- voltage barriers: reference voltage_barrier/{l1,l2,bowl,bump,courant_beltrami}.py ----
@@ -83,9 +102,8 @@ __device__ __forceinline__ void stage_hot_static(unsigned char* smem_dst, const 
         "l"(gsrc), "r"(bytes), "r"(bar_a)
         : "memory");
   }
-  // every thread waits for phase 0 of the barrier
   uint32_t done = 0;
-  while (!done) {
+  while (!done) {   // every thread waits for phase 0 of the barrier
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
@@ -98,13 +116,15 @@ __device__ __forceinline__ void stage_hot_static(unsigned char* smem_dst, const 
 
 // Views of the staged static blob and of one env's shared-memory slab.
 struct Hot {
-  const double *gu, *bu, *gd, *bd, *gii, *bii;
-  const uint16_t *parent, *cstart, *eorder, *elev, *dlev;
+  const double2 *yup, *ydn, *yii, *ysl;
+  const uint64_t *ndesc, *edesc;
+  const uint16_t *enode, *elev, *dlev, *lptr, *lidx, *sptr, *sidx, *xptr, *xidx, *node_of_bus, *obs_off;
 };
 struct Slab {
-  double* a[kNodeArrays];
-  double* pv;   // sgen.p_mw   [n_sgen]
-  double* q;    // sgen.q_mvar [n_sgen]
+  double2* a[kNodeArrays2];
+  double* base;   // the slab as a flat double array (obs program offsets index this)
+  double* pv;     // sgen.p_mw   [n_sgen]
+  double* q;      // sgen.q_mvar [n_sgen]
 };
 
 // ------------------------------------------------------------------------------------------
@@ -116,116 +136,139 @@ struct Slab {
 // ------------------------------------------------------------------------------------------
 template <int G>
 __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Slab& s, int gl, bool skip, int& iters) {
-  const int n = p.n;
-  double* vm = s.a[A_VM]; double* va = s.a[A_VA]; double* e = s.a[A_E]; double* f = s.a[A_F];
-  double* aup = s.a[A_AUP]; double* bup = s.a[A_BUP]; double* adn = s.a[A_ADN]; double* bdn = s.a[A_BDN];
-  double* d0 = s.a[A_D0]; double* d1 = s.a[A_D1]; double* d2 = s.a[A_D2]; double* d3 = s.a[A_D3];
-  double* r0 = s.a[A_R0]; double* r1 = s.a[A_R1];
-  double* s0 = s.a[A_S0]; double* s1 = s.a[A_S1]; double* s2 = s.a[A_S2]; double* s3 = s.a[A_S3];
-  double* t0 = s.a[A_T0]; double* t1 = s.a[A_T1];
-  const double* ps = s.a[A_PS]; const double* qs = s.a[A_QS];
+  const int npq = p.npq;
+  double2* VV = s.a[A_VV]; double2* EF = s.a[A_EF]; const double2* SP = s.a[A_SP];
+  double2* UP = s.a[A_UP]; double2* DN = s.a[A_DN]; double2* T = s.a[A_T];
+  double2* D01 = s.a[A_D01]; double2* D23 = s.a[A_D23]; double2* R = s.a[A_R];
 
-  // flat start (pandapower init="auto"): |V| = vm_init, angle 0 on PQ buses; slack fixed
-  for (int i = gl; i < n; i += G) {
-    const bool root = (i == 0);
-    vm[i] = root ? p.vm0 : p.vm_init;
-    va[i] = root ? p.va0 : 0.0;
-    e[i] = root ? p.e0 : p.vm_init;
-    f[i] = root ? p.f0 : 0.0;
+  // flat start (pandapower init="auto"): |V| = vm_init, angle 0 on every PQ bus; sentinel slots
+  for (int i = gl; i <= npq; i += G) {
+    const bool sl = (i == npq);
+    VV[i] = sl ? make_double2(p.vm0, p.va0) : make_double2(p.vm_init, 0.0);
+    EF[i] = sl ? make_double2(p.e0, p.f0) : make_double2(p.vm_init, 0.0);
+    UP[i] = make_double2(0.0, 0.0);      // roots keep zeros here; slot npq is the "no child" slot
+    DN[i] = make_double2(0.0, 0.0);
+    T[i] = make_double2(0.0, 0.0);
   }
   __syncwarp();
 
   bool done = skip;      // this group's env converged (idle groups never hold the warp back)
   int it = 0;
   iters = 0;
+  const double2 v0 = make_double2(p.e0, p.f0);
   while (true) {
-    // --- per-edge terms (row i / col parent and row parent / col i) ---
-    for (int i = 1 + gl; i < n; i += G) {
-      const int pa = h.parent[i];
-      const double ei = e[i], fi = f[i], ep = e[pa], fp = f[pa];
-      const double cc = ei * ep + fi * fp;        // ViVp cos(ti - tp)
-      const double ss = fi * ep - ei * fp;        // ViVp sin(ti - tp)
-      const double gu = h.gu[i], bu = h.bu[i], gd = h.gd[i], bd = h.bd[i];
-      aup[i] = gu * ss - bu * cc;
-      bup[i] = gu * cc + bu * ss;
-      adn[i] = -gd * ss - bd * cc;
-      bdn[i] = gd * cc - bd * ss;
+    // --- per-edge terms of (i, parent): row i / col parent and row parent / col i ---
+#pragma unroll 2
+    for (int i = gl; i < npq; i += G) {
+      const uint32_t pa = static_cast<uint32_t>(h.ndesc[i]) & 0xFFFFu;
+      if (pa != kNone) {
+        const double2 vi = EF[i], vp = EF[pa];
+        const double cc = vi.x * vp.x + vi.y * vp.y;       // ViVp cos(ti - tp)
+        const double ss = vi.y * vp.x - vi.x * vp.y;       // ViVp sin(ti - tp)
+        const double2 yu = h.yup[i], yd = h.ydn[i];
+        UP[i] = make_double2(yu.x * ss - yu.y * cc, yu.x * cc + yu.y * ss);
+        DN[i] = make_double2(-yd.x * ss - yd.y * cc, yd.x * cc - yd.y * ss);
+      }
     }
     __syncwarp();
     // --- mismatch F = S_calc - S_spec and diagonal Jacobian blocks ---
     double nrm = 0.0;
-    for (int i = 1 + gl; i < n; i += G) {
-      double sa = 0.0, sb = 0.0;
-      for (int c = h.cstart[i], ce = h.cstart[i + 1]; c < ce; ++c) { sa += adn[c]; sb += bdn[c]; }
-      const double vv = e[i] * e[i] + f[i] * f[i];
-      const double gv = h.gii[i] * vv, bv = h.bii[i] * vv;
-      const double P = gv + bup[i] + sb;
-      const double Q = -bv + aup[i] + sa;
-      const double Fp = P - ps[i], Fq = Q - qs[i];
-      d0[i] = -Q - bv;   // dP/dtheta
-      d1[i] = P + gv;    // dP/dV * V
-      d2[i] = P - gv;    // dQ/dtheta
-      d3[i] = Q - bv;    // dQ/dV * V
-      r0[i] = -Fp;
-      r1[i] = -Fq;
+#pragma unroll 2
+    for (int i = gl; i < npq; i += G) {
+      const uint64_t nd = h.ndesc[i];
+      const int c0 = static_cast<int>((nd >> 16) & 0xFFFFu), c1 = static_cast<int>((nd >> 32) & 0xFFFFu);
+      const int nx = static_cast<int>(nd >> 48);
+      const double2 vi = EF[i];
+      const double2 ys = h.ysl[i];                       // zero unless the bus is adjacent to the slack
+      const double cs0 = vi.x * v0.x + vi.y * v0.y, sn0 = vi.y * v0.x - vi.x * v0.y;
+      const double2 u = UP[i], a0 = DN[c0], a1 = DN[c1];  // roots: UP = 0; missing children: zero slot
+      double sa = ys.x * sn0 - ys.y * cs0 + u.x + a0.x + a1.x;
+      double sb = ys.x * cs0 + ys.y * sn0 + u.y + a0.y + a1.y;
+#pragma unroll 1
+      for (int c = c1 + 1; c <= c1 + nx; ++c) { const double2 d = DN[c]; sa += d.x; sb += d.y; }
+      const double vv = vi.x * vi.x + vi.y * vi.y;
+      const double2 yi = h.yii[i];
+      const double gv = yi.x * vv, bv = yi.y * vv;
+      const double P = gv + sb, Q = sa - bv;
+      const double2 sp = SP[i];
+      const double Fp = P - sp.x, Fq = Q - sp.y;
+      D01[i] = make_double2(-Q - bv, P + gv);     // dP/dtheta, dP/dV * V
+      D23[i] = make_double2(P - gv, Q - bv);      // dQ/dtheta, dQ/dV * V
+      R[i] = make_double2(-Fp, -Fq);
       nrm = nanmax(nrm, nanmax(fabs(Fp), fabs(Fq)));
     }
     nrm = group_nanmax<G>(nrm);
-    if (!done) {
-      if (nrm < p.tol) { done = true; iters = it; }
-    }
-    const bool all_done = __all_sync(kFull, done);
-    if (all_done || it >= p.max_iter) break;
+    if (!done && nrm < p.tol) { done = true; iters = it; }
+    if (__all_sync(kFull, done) || it >= p.max_iter) break;
     ++it;
     __syncwarp();
     // --- forward elimination, leaves first (levels of equal height) ---
-    for (int lev = 0; lev < p.n_elev; ++lev) {
+    for (int lev = 0; lev < p.n_lev; ++lev) {
+#pragma unroll 1
       for (int idx = h.elev[lev] + gl, ie = h.elev[lev + 1]; idx < ie; idx += G) {
-        const int i = h.eorder[idx];
-        double D0 = d0[i], D1 = d1[i], D2 = d2[i], D3 = d3[i], R0 = r0[i], R1 = r1[i];
-        for (int c = h.cstart[i], ce = h.cstart[i + 1]; c < ce; ++c) {
-          D0 -= s0[c]; D1 -= s1[c]; D2 -= s2[c]; D3 -= s3[c];
-          R0 -= t0[c]; R1 -= t1[c];
+        const int i = h.enode[idx];
+        const uint64_t ed = h.edesc[idx];
+        const int c0 = static_cast<int>((ed >> 16) & 0xFFFFu), c1 = static_cast<int>((ed >> 32) & 0xFFFFu);
+        const int nx = static_cast<int>(ed >> 48);
+        double2 d01 = D01[i], d23 = D23[i], r = R[i];
+        {   // children's Schur updates (aliased arrays); a missing child reads the zero slot
+          const double2 p01 = UP[c0], p23 = DN[c0], pt = T[c0], q01 = UP[c1], q23 = DN[c1], qt = T[c1];
+          d01.x -= p01.x + q01.x; d01.y -= p01.y + q01.y;
+          d23.x -= p23.x + q23.x; d23.y -= p23.y + q23.y;
+          r.x -= pt.x + qt.x; r.y -= pt.y + qt.y;
         }
-        const double idet = 1.0 / (D0 * D3 - D1 * D2);
-        const double i00 = D3 * idet, i01 = -D1 * idet, i10 = -D2 * idet, i11 = D0 * idet;
-        const double c0 = i00 * R0 + i01 * R1, c1 = i10 * R0 + i11 * R1;
-        r0[i] = c0; r1[i] = c1;                       // D^-1 r  (becomes dx in the back sweep)
-        if (h.parent[i] != 0) {
-          const double au = aup[i], bu = bup[i];      // J[i,parent] = [[au, bu], [-bu, au]]
-          const double m00 = i00 * au - i01 * bu, m01 = i00 * bu + i01 * au;
-          const double m10 = i10 * au - i11 * bu, m11 = i10 * bu + i11 * au;
-          d0[i] = m00; d1[i] = m01; d2[i] = m10; d3[i] = m11;   // D^-1 J[i,parent]
-          const double ad = adn[i], bd = bdn[i];      // J[parent,i] = [[ad, bd], [-bd, ad]]
-          s0[i] = ad * m00 + bd * m10;  s1[i] = ad * m01 + bd * m11;
-          s2[i] = -bd * m00 + ad * m10; s3[i] = -bd * m01 + ad * m11;
-          t0[i] = ad * c0 + bd * c1;    t1[i] = -bd * c0 + ad * c1;
+#pragma unroll 1
+        for (int c = c1 + 1; c <= c1 + nx; ++c) {
+          const double2 s01 = UP[c], s23 = DN[c], t = T[c];
+          d01.x -= s01.x; d01.y -= s01.y; d23.x -= s23.x; d23.y -= s23.y;
+          r.x -= t.x; r.y -= t.y;
         }
+        const double2 u = UP[i], d = DN[i];            // J[i,p] = [[a,b],[-b,a]](u), J[p,i] likewise (d); roots: 0
+        // adjugate form: everything that does not need 1/det runs beside the reciprocal
+        const double idet = fast_rcp(d01.x * d23.y - d01.y * d23.x);
+        const double ca0 = d23.y * r.x - d01.y * r.y, ca1 = d01.x * r.y - d23.x * r.x;   // adj(D) r
+        const double ma00 = d23.y * u.x + d01.y * u.y, ma01 = d23.y * u.y - d01.y * u.x; // adj(D) J[i,p]
+        const double ma10 = -d23.x * u.x - d01.x * u.y, ma11 = d01.x * u.x - d23.x * u.y;
+        const double sa00 = d.x * ma00 + d.y * ma10, sa01 = d.x * ma01 + d.y * ma11;     // J[p,i] adj(D) J[i,p]
+        const double sa10 = d.x * ma10 - d.y * ma00, sa11 = d.x * ma11 - d.y * ma01;
+        const double ta0 = d.x * ca0 + d.y * ca1, ta1 = d.x * ca1 - d.y * ca0;           // J[p,i] adj(D) r
+        R[i] = make_double2(ca0 * idet, ca1 * idet);           // D^-1 r  (becomes dx in the back sweep)
+        D01[i] = make_double2(ma00 * idet, ma01 * idet);       // D^-1 J[i,p]
+        D23[i] = make_double2(ma10 * idet, ma11 * idet);
+        UP[i] = make_double2(sa00 * idet, sa01 * idet);        // Schur update for the parent (zero at roots)
+        DN[i] = make_double2(sa10 * idet, sa11 * idet);
+        T[i] = make_double2(ta0 * idet, ta1 * idet);
       }
       __syncwarp();
     }
-    // --- back substitution by depth (BFS numbering: a depth level is a contiguous range);
-    //     fused with the state update and V = Vm * exp(j*theta) ---
-    for (int d = 1; d < p.n_dlev; ++d) {
+    // --- back substitution by depth (a depth level is a contiguous node range) ---
+    for (int d = 1; d < p.n_lev; ++d) {
+#pragma unroll 1
       for (int i = h.dlev[d] + gl, ie = h.dlev[d + 1]; i < ie; i += G) {
-        double x0 = r0[i], x1 = r1[i];
-        const int pa = h.parent[i];
-        if (pa != 0) {
-          const double xp0 = r0[pa], xp1 = r1[pa];
-          x0 -= d0[i] * xp0 + d1[i] * xp1;
-          x1 -= d2[i] * xp0 + d3[i] * xp1;
-          r0[i] = x0; r1[i] = x1;
-        }
-        if (!done) {
-          const double th = va[i] + x0;
-          const double v = vm[i] + vm[i] * x1;
-          double sn, cs;
-          sincos(th, &sn, &cs);
-          va[i] = th; vm[i] = v; e[i] = v * cs; f[i] = v * sn;
-        }
+        const uint32_t pa = static_cast<uint32_t>(h.ndesc[i]) & 0xFFFFu;   // depth >= 1: always has a parent
+        const double2 xp = R[pa], m01 = D01[i], m23 = D23[i];
+        double2 x = R[i];
+        x.x -= m01.x * xp.x + m01.y * xp.y;
+        x.y -= m23.x * xp.x + m23.y * xp.y;
+        R[i] = x;
       }
       __syncwarp();
     }
+    // --- update (theta += dtheta, V += V * dV/V) and V = Vm exp(j theta) ---
+#pragma unroll 2
+    for (int i = gl; i < npq; i += G) {
+      if (!done) {
+        const double2 x = R[i];
+        double2 v = VV[i];
+        v.y += x.x;
+        v.x += v.x * x.y;
+        double sn, cs;
+        sincos(v.y, &sn, &cs);
+        VV[i] = v;
+        EF[i] = make_double2(v.x * cs, v.x * sn);
+      }
+    }
+    __syncwarp();
   }
   return done;
 }
@@ -233,53 +276,6 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
 // sgen.q_mvar from an action: reference _clip_reactive_power :568-572
 __device__ __forceinline__ double clip_q(double a, double pv, double smax) {
   return sqrt(smax * smax - pv * pv) * a;
-}
-
-// Per-unit edge terms + e,f from (vm, va) - used when the previous solution is reloaded from HBM
-// (divergence branch, reference :188-196).
-template <int G>
-__device__ __forceinline__ void recompute_edges(const Params& p, const Hot& h, const Slab& s, int gl) {
-  const int n = p.n;
-  for (int i = gl; i < n; i += G) {
-    double sn, cs;
-    sincos(s.a[A_VA][i], &sn, &cs);
-    s.a[A_E][i] = s.a[A_VM][i] * cs;
-    s.a[A_F][i] = s.a[A_VM][i] * sn;
-  }
-  __syncwarp();
-  for (int i = 1 + gl; i < n; i += G) {
-    const int pa = h.parent[i];
-    const double ei = s.a[A_E][i], fi = s.a[A_F][i], ep = s.a[A_E][pa], fp = s.a[A_F][pa];
-    const double cc = ei * ep + fi * fp, ss = fi * ep - ei * fp;
-    s.a[A_ADN][i] = -h.gd[i] * ss - h.bd[i] * cc;
-    s.a[A_BDN][i] = h.gd[i] * cc - h.bd[i] * ss;
-  }
-  __syncwarp();
-}
-
-// One observation entry (reference get_obs :232-274):
-// obs_i = [P_zone | Q_zone | pv_i | q_i | vm_zone | va_zone (rad)], zero padded.
-// P_zone = res_bus.p_mw + sum of sgen.p_mw of the zone's sgens on that bus (the 15/03/24 fix).
-template <class BusP, class BusQ, class BusVm, class BusVa, class SgP, class SgQ>
-__device__ __forceinline__ double obs_entry(const Params& p, int agent, int k, BusP busp, BusQ busq, BusVm busvm,
-                                            BusVa busva, SgP sgp, SgQ sgq) {
-  const int z0 = __ldg(p.zptr + agent), nz = __ldg(p.zptr + agent + 1) - z0;
-  if (k < 2 * nz) {
-    const bool isq = k >= nz;
-    const int slot = z0 + (isq ? k - nz : k);
-    const int node = __ldg(p.znode + slot);
-    double v = isq ? busq(node) : busp(node);
-    for (int j = __ldg(p.zsg_ptr + slot), je = __ldg(p.zsg_ptr + slot + 1); j < je; ++j) {
-      const int sg = __ldg(p.zsg_idx + j);
-      v += isq ? sgq(sg) : sgp(sg);
-    }
-    return v;
-  }
-  if (k == 2 * nz) return sgp(agent);
-  if (k == 2 * nz + 1) return sgq(agent);
-  if (k < 3 * nz + 2) return busvm(__ldg(p.znode + z0 + k - 2 * nz - 2));
-  if (k < 4 * nz + 2) return busva(__ldg(p.znode + z0 + k - 3 * nz - 2));
-  return 0.0;
 }
 
 template <int G, int MODE>
@@ -290,30 +286,39 @@ __global__ void __launch_bounds__(128) env_kernel(const __grid_constant__ Params
 
   const HotLayout& hl = p.hot_layout;
   Hot h;
-  h.gu = reinterpret_cast<const double*>(smem_raw + hl.gu);
-  h.bu = reinterpret_cast<const double*>(smem_raw + hl.bu);
-  h.gd = reinterpret_cast<const double*>(smem_raw + hl.gd);
-  h.bd = reinterpret_cast<const double*>(smem_raw + hl.bd);
-  h.gii = reinterpret_cast<const double*>(smem_raw + hl.gii);
-  h.bii = reinterpret_cast<const double*>(smem_raw + hl.bii);
-  h.parent = reinterpret_cast<const uint16_t*>(smem_raw + hl.parent);
-  h.cstart = reinterpret_cast<const uint16_t*>(smem_raw + hl.cstart);
-  h.eorder = reinterpret_cast<const uint16_t*>(smem_raw + hl.eorder);
+  h.yup = reinterpret_cast<const double2*>(smem_raw + hl.yup);
+  h.ydn = reinterpret_cast<const double2*>(smem_raw + hl.ydn);
+  h.yii = reinterpret_cast<const double2*>(smem_raw + hl.yii);
+  h.ysl = reinterpret_cast<const double2*>(smem_raw + hl.ysl);
+  h.ndesc = reinterpret_cast<const uint64_t*>(smem_raw + hl.ndesc);
+  h.edesc = reinterpret_cast<const uint64_t*>(smem_raw + hl.edesc);
+  h.enode = reinterpret_cast<const uint16_t*>(smem_raw + hl.enode);
   h.elev = reinterpret_cast<const uint16_t*>(smem_raw + hl.elev);
   h.dlev = reinterpret_cast<const uint16_t*>(smem_raw + hl.dlev);
+  h.lptr = reinterpret_cast<const uint16_t*>(smem_raw + hl.lptr);
+  h.lidx = reinterpret_cast<const uint16_t*>(smem_raw + hl.lidx);
+  h.sptr = reinterpret_cast<const uint16_t*>(smem_raw + hl.sptr);
+  h.sidx = reinterpret_cast<const uint16_t*>(smem_raw + hl.sidx);
+  h.xptr = reinterpret_cast<const uint16_t*>(smem_raw + hl.xptr);
+  h.xidx = reinterpret_cast<const uint16_t*>(smem_raw + hl.xidx);
+  h.node_of_bus = reinterpret_cast<const uint16_t*>(smem_raw + hl.node_of_bus);
+  h.obs_off = reinterpret_cast<const uint16_t*>(smem_raw + hl.obs_off);
 
   const int gl = threadIdx.x % G;
   const int gidx = threadIdx.x / G;
   const int epb = blockDim.x / G;
+  const int npq = p.npq, n = p.n_bus, nl = p.n_load, ng = p.n_sgen, na = npq + 1;
   Slab s;
   {
-    double* base = reinterpret_cast<double*>(smem_raw + hl.bytes) + static_cast<size_t>(gidx) * p.env_stride;
+    double2* base = reinterpret_cast<double2*>(smem_raw + hl.bytes) + static_cast<size_t>(gidx) * p.env_stride2;
 #pragma unroll
-    for (int a = 0; a < kNodeArrays; ++a) s.a[a] = base + a * p.n_pad;
-    s.pv = base + kNodeArrays * p.n_pad;
-    s.q = s.pv + p.n_sgen_pad;
+    for (int a = 0; a < kNodeArrays2; ++a) s.a[a] = base + a * na;
+    s.base = reinterpret_cast<double*>(base);
+    s.pv = reinterpret_cast<double*>(base + p.pvq_off2);
+    s.q = s.pv + ng;
   }
-  const int n = p.n, nl = p.n_load, ng = p.n_sgen;
+  double* stage_pl = reinterpret_cast<double*>(s.a[A_UP]);   // scratch of the prologue: scaled load p / q
+  double* stage_ql = stage_pl + nl;
   const uint32_t k0 = static_cast<uint32_t>(p.seed), k1 = static_cast<uint32_t>(p.seed >> 32);
 
   for (int base = blockIdx.x * epb; base < p.nb; base += gridDim.x * epb) {
@@ -356,6 +361,8 @@ __global__ void __launch_bounds__(128) env_kernel(const __grid_constant__ Params
       long long row = 0;
       if (MODE == MODE_RESET) { row = start + 1; if (row > p.n_rows - 1) row = p.n_rows - 1; }   // t = steps = 1
       const uint32_t c1 = kResetFlag | static_cast<uint32_t>(attempt);
+      // (1) coalesced, independent loads of the env's element values into shared memory
+#pragma unroll 2
       for (int j = gl; j < ng; j += G) {
         double pv, q;
         if (MODE == MODE_SOLVE) {
@@ -376,33 +383,36 @@ __global__ void __launch_bounds__(128) env_kernel(const __grid_constant__ Params
         }
         s.pv[j] = pv; s.q[j] = q;
       }
-      __syncwarp();
-      for (int i = gl; i < n; i += G) {             // A.1: PD/QD per bus, Sbus = -(PD + jQD)/baseMVA
-        double pd = 0.0, qd = 0.0;
-        for (int t = __ldg(p.lptr + i), te = __ldg(p.lptr + i + 1); t < te; ++t) {
-          const int l = __ldg(p.lidx + t);
-          double pl, ql;
-          if (MODE == MODE_SOLVE) { pl = p.in_pl[eL + l]; ql = p.in_ql[eL + l]; }
-          else if (MODE == MODE_STEP) { pl = p.cur_pl[eL + l]; ql = p.cur_ql[eL + l]; }
-          else {
-            pl = __ldg(p.prof_lp + row * nl + l);
-            ql = __ldg(p.prof_lq + row * nl + l);
-            if (p.add_noise) {                                                   // :503, :508
-              pl += __ldg(p.lp_std + l) * half_normal(key, c1, ng + l);
-              ql += __ldg(p.lq_std + l) * half_normal(key, c1, ng + nl + l);
-            }
-            if (valid) { p.cur_pl[eL + l] = pl; p.cur_ql[eL + l] = ql; }
+#pragma unroll 4
+      for (int l = gl; l < nl; l += G) {
+        double pl, ql;
+        if (MODE == MODE_SOLVE) { pl = p.in_pl[eL + l]; ql = p.in_ql[eL + l]; }
+        else if (MODE == MODE_STEP) { pl = p.cur_pl[eL + l]; ql = p.cur_ql[eL + l]; }
+        else {
+          pl = __ldg(p.prof_lp + row * nl + l);
+          ql = __ldg(p.prof_lq + row * nl + l);
+          if (p.add_noise) {                                                   // :503, :508
+            pl += __ldg(p.lp_std + l) * half_normal(key, c1, ng + l);
+            ql += __ldg(p.lq_std + l) * half_normal(key, c1, ng + nl + l);
           }
-          const double sc = __ldg(p.lscale + l);
-          pd += pl * sc; qd += ql * sc;
+          if (valid) { p.cur_pl[eL + l] = pl; p.cur_ql[eL + l] = ql; }
         }
-        for (int t = __ldg(p.sptr + i), te = __ldg(p.sptr + i + 1); t < te; ++t) {
-          const int g = __ldg(p.sidx + t);
+        const double sc = __ldg(p.lscale + l);
+        stage_pl[l] = pl * sc; stage_ql[l] = ql * sc;
+      }
+      __syncwarp();
+      // (2) A.1: PD/QD per bus, Sbus = -(PD + jQD)/baseMVA
+      for (int i = gl; i < npq; i += G) {
+        double pd = 0.0, qd = 0.0;
+#pragma unroll 1
+        for (int t = h.lptr[i], te = h.lptr[i + 1]; t < te; ++t) { const int l = h.lidx[t]; pd += stage_pl[l]; qd += stage_ql[l]; }
+#pragma unroll 1
+        for (int t = h.sptr[i], te = h.sptr[i + 1]; t < te; ++t) {
+          const int g = h.sidx[t];
           const double sc = __ldg(p.sscale + g);
           pd -= s.pv[g] * sc; qd -= s.q[g] * sc;
         }
-        s.a[A_PS][i] = -pd * p.inv_base;
-        s.a[A_QS][i] = -qd * p.inv_base;
+        s.a[A_SP][i] = make_double2(-pd * p.inv_base, -qd * p.inv_base);
       }
       __syncwarp();
 
@@ -416,52 +426,109 @@ __global__ void __launch_bounds__(128) env_kernel(const __grid_constant__ Params
     }
 
     // ---------------- epilogue ----------------
+    double2* VV = s.a[A_VV]; double2* EF = s.a[A_EF]; double2* SP = s.a[A_SP];
+    double2* BP = s.a[A_BP]; double2* OP = s.a[A_OP];
     // divergence branch (reference :188-196): fall back to the previous solution kept in HBM
     if (MODE == MODE_STEP && !conv) {
-      for (int i = gl; i < n; i += G) {
+      for (int i = gl; i < npq; i += G) {
         const int b = __ldg(p.bus_of_node + i);
-        s.a[A_VM][i] = p.res_vm[eN + b];
-        s.a[A_VA][i] = p.res_va[eN + b];
-        s.a[A_PS][i] = -p.res_p[eN + b] * p.inv_base;
-        s.a[A_QS][i] = -p.res_q[eN + b] * p.inv_base;
+        const double vm = p.res_vm[eN + b], va = p.res_va[eN + b];
+        double sn, cs;
+        sincos(va, &sn, &cs);
+        VV[i] = make_double2(vm, va);
+        EF[i] = make_double2(vm * cs, vm * sn);
+        SP[i] = make_double2(-p.res_p[eN + b] * p.inv_base, -p.res_q[eN + b] * p.inv_base);
       }
     }
     __syncwarp();
-    if (MODE == MODE_STEP && !__all_sync(kFull, conv)) {
-      // (warp-uniform branch) rebuild e,f and the edge terms for the groups that reloaded; the
-      // converged groups recompute identical values
-      recompute_edges<G>(p, h, s, gl);
-    }
     const bool write_res = valid && (MODE != MODE_STEP || conv);
 
-    // slack injection (pfsoln): S0 = V0 conj(Ybus[0,:] V)
-    double P0, Q0;
+    // slack injection (pfsoln): S0 = V0 conj(Ybus[0,:] V) -> sentinel slot of SP
     {
-      double sa = 0.0, sb = 0.0;
-      for (int c = h.cstart[0], ce = h.cstart[1]; c < ce; ++c) { sa += s.a[A_ADN][c]; sb += s.a[A_BDN][c]; }
       const double vv = p.vm0 * p.vm0;
-      P0 = h.gii[0] * vv + sb;
-      Q0 = -h.bii[0] * vv + sa;
+      double P0 = p.ysl_g0 * vv, Q0 = -p.ysl_b0 * vv;
+      for (int k = 0; k < p.n_slack_adj; ++k) {
+        const int i = __ldg(p.sl_node + k);
+        const double g = __ldg(p.sl_y + 2 * k), b = __ldg(p.sl_y + 2 * k + 1);
+        const double2 vi = EF[i];
+        const double cc = p.e0 * vi.x + p.f0 * vi.y, ss = p.f0 * vi.x - p.e0 * vi.y;   // V0 Vi cos/sin(t0 - ti)
+        P0 += g * cc + b * ss;
+        Q0 += g * ss - b * cc;
+      }
+      if (gl == 0) SP[npq] = make_double2(P0, Q0);
     }
-    constexpr double kRad2Deg = 57.295779513082320876798;
+    // sgen.q_mvar after the step: the clipped action, or the previous q on divergence (:189-196)
+    double sum_q_eff = 0.0, sum_q_try = 0.0;
+    if (MODE == MODE_STEP) {
+      for (int j = gl; j < ng; j += G) {
+        const double q_try = s.q[j];
+        const double q_eff = conv ? q_try : p.cur_q[eG + j];
+        sum_q_try += fabs(q_try);
+        sum_q_eff += fabs(q_eff * __ldg(p.sscale + j));     // res_sgen.q_mvar = q * scaling (:604-605)
+        s.q[j] = q_eff;
+        if (write_res) p.cur_q[eG + j] = q_eff;
+      }
+    }
+    // next profile row (reference _set_demand_and_pv :491-513): t = self.steps before the increment.
+    // Elements [pv | load_p | load_q] are drawn in Box-Muller pairs (2m, 2m+1).
+    if (MODE == MODE_STEP) {
+      long long nrow = start + steps_old;
+      if (nrow > p.n_rows - 1) nrow = p.n_rows - 1;
+      const uint32_t c1 = static_cast<uint32_t>(steps_old);
+      const int n_elem = ng + 2 * nl;
+#pragma unroll 2
+      for (int m = gl; 2 * m < n_elem; m += G) {
+        double z[2] = {0.0, 0.0};
+        if (p.add_noise) half_normal_pair(key, c1, m, z[0], z[1]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int el = 2 * m + u;
+          if (el >= n_elem) break;
+          if (el < ng) {
+            const double pv = __ldg(p.prof_pv + nrow * ng + el) + __ldg(p.pv_std + el) * z[u];
+            s.pv[el] = pv;
+            if (valid) p.cur_pv[eG + el] = pv;
+          } else if (el < ng + nl) {
+            const int l = el - ng;
+            const double pl = __ldg(p.prof_lp + nrow * nl + l) + __ldg(p.lp_std + l) * z[u];
+            if (valid) p.cur_pl[eL + l] = pl;
+          } else {
+            const int l = el - ng - nl;
+            const double ql = __ldg(p.prof_lq + nrow * nl + l) + __ldg(p.lq_std + l) * z[u];
+            if (valid) p.cur_ql[eL + l] = ql;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // res_bus columns per node (BP) and the "demand" columns of get_obs (OP = BP + sgens of the bus's own zone)
+    for (int i = gl; i <= npq; i += G) {
+      const double2 sp = SP[i];
+      const double2 bp = make_double2(-sp.x * p.base_mva, -sp.y * p.base_mva);
+      double2 op = bp;
+#pragma unroll 1
+      for (int t = h.xptr[i], te = h.xptr[i + 1]; t < te; ++t) { const int g = h.xidx[t]; op.x += s.pv[g]; op.y += s.q[g]; }
+      BP[i] = bp; OP[i] = op;
+    }
+    __syncwarp();
     // per-bus results + voltage statistics (reference _calc_reward :584-596, :610)
     double cnt_lo = 0, cnt_hi = 0, sum_dev = 0, sum_v = 0, max_drop = 0, max_rise = 0, sum_bar = 0;
     const double v_ref = 0.5 * (p.v_lower + p.v_upper);
+#pragma unroll 2
     for (int b = gl; b < n; b += G) {
-      const int i = __ldg(p.node_of_bus + b);
-      const double v = s.a[A_VM][i], th = s.a[A_VA][i];
-      const double pb = (i == 0) ? -P0 * p.base_mva : -s.a[A_PS][i] * p.base_mva;
-      const double qb = (i == 0) ? -Q0 * p.base_mva : -s.a[A_QS][i] * p.base_mva;
+      const int i = h.node_of_bus[b];
+      const double2 vv = VV[i], bp = BP[i];
+      const double v = vv.x, th = vv.y;
       if (MODE == MODE_SOLVE) {
         if (valid) {
           if (p.out_vm) p.out_vm[eN + b] = v;
           if (p.out_va) p.out_va[eN + b] = th * kRad2Deg;
-          if (p.out_p) p.out_p[eN + b] = pb;
-          if (p.out_q) p.out_q[eN + b] = qb;
+          if (p.out_p) p.out_p[eN + b] = bp.x;
+          if (p.out_q) p.out_q[eN + b] = bp.y;
         }
       } else {
         if (write_res) {
-          p.res_vm[eN + b] = v; p.res_va[eN + b] = th; p.res_p[eN + b] = pb; p.res_q[eN + b] = qb;
+          p.res_vm[eN + b] = v; p.res_va[eN + b] = th; p.res_p[eN + b] = bp.x; p.res_q[eN + b] = bp.y;
         }
         if (MODE == MODE_STEP) {
           cnt_lo += (v < p.v_lower) ? 1.0 : 0.0;
@@ -478,12 +545,13 @@ __global__ void __launch_bounds__(128) env_kernel(const __grid_constant__ Params
     double sum_pl = 0.0;
     {
       const size_t ePL = static_cast<size_t>(env) * p.n_line;
+#pragma unroll 2
       for (int k = gl; k < p.n_line; k += G) {
         const int nf = __ldg(p.line_f + k), nt = __ldg(p.line_t + k);
-        const double ef = s.a[A_E][nf], ff = s.a[A_F][nf], et = s.a[A_E][nt], ft = s.a[A_F][nt];
-        const double cc = ef * et + ff * ft, ss = ff * et - ef * ft;
+        const double2 vf = EF[nf], vt = EF[nt];
+        const double cc = vf.x * vt.x + vf.y * vt.y, ss = vf.y * vt.x - vf.x * vt.y;
         const double* c = p.line_c + 4 * k;
-        const double pl = __ldg(c) * (ef * ef + ff * ff) + __ldg(c + 1) * (et * et + ft * ft) +
+        const double pl = __ldg(c) * (vf.x * vf.x + vf.y * vf.y) + __ldg(c + 1) * (vt.x * vt.x + vt.y * vt.y) +
                           __ldg(c + 2) * cc + __ldg(c + 3) * ss;
         sum_pl += pl;
         if (MODE == MODE_SOLVE) { if (valid && p.out_pl) p.out_pl[ePL + k] = pl; }
@@ -500,17 +568,6 @@ __global__ void __launch_bounds__(128) env_kernel(const __grid_constant__ Params
     }
 
     if (MODE == MODE_STEP) {
-      // q terms: res_sgen.q_mvar = sgen.q_mvar * scaling (:604-605); on divergence the reward uses
-      // the previous q, info["q_loss"] the attempted one (:189-196)
-      double sum_q_eff = 0.0, sum_q_try = 0.0;
-      for (int j = gl; j < ng; j += G) {
-        const double q_try = s.q[j];
-        const double q_eff = conv ? q_try : p.cur_q[eG + j];
-        sum_q_try += fabs(q_try);
-        sum_q_eff += fabs(q_eff * __ldg(p.sscale + j));
-        s.q[j] = q_eff;                                  // sgen.q_mvar after the step (rolled back on failure)
-        if (write_res) p.cur_q[eG + j] = q_eff;
-      }
       cnt_lo = group_sum<G>(cnt_lo); cnt_hi = group_sum<G>(cnt_hi);
       sum_dev = group_sum<G>(sum_dev); sum_v = group_sum<G>(sum_v); sum_bar = group_sum<G>(sum_bar);
       max_drop = group_max<G>(max_drop); max_rise = group_max<G>(max_rise);
@@ -537,24 +594,6 @@ __global__ void __launch_bounds__(128) env_kernel(const __grid_constant__ Params
           o[8] = sum_pl; o[9] = conv ? q_loss : sum_q_try / ng; o[10] = conv ? 0.0 : 1.0;
         }
       }
-      // next profile row (reference _set_demand_and_pv :491-513): t = self.steps before the increment
-      long long nrow = start + steps_old;
-      if (nrow > p.n_rows - 1) nrow = p.n_rows - 1;
-      const uint32_t c1 = static_cast<uint32_t>(steps_old);
-      for (int j = gl; j < ng; j += G) {
-        double pv = __ldg(p.prof_pv + nrow * ng + j);
-        if (p.add_noise) pv += __ldg(p.pv_std + j) * half_normal(key, c1, j);
-        s.pv[j] = pv;
-        if (valid) p.cur_pv[eG + j] = pv;
-      }
-      for (int l = gl; l < nl; l += G) {
-        double pl = __ldg(p.prof_lp + nrow * nl + l), ql = __ldg(p.prof_lq + nrow * nl + l);
-        if (p.add_noise) {
-          pl += __ldg(p.lp_std + l) * half_normal(key, c1, ng + l);
-          ql += __ldg(p.lq_std + l) * half_normal(key, c1, ng + nl + l);
-        }
-        if (valid) { p.cur_pl[eL + l] = pl; p.cur_ql[eL + l] = ql; }
-      }
     } else {  // MODE_RESET
       for (int j = gl; j < ng; j += G) if (valid) p.cur_q[eG + j] = s.q[j];
       if (valid && gl == 0) {
@@ -564,37 +603,25 @@ __global__ void __launch_bounds__(128) env_kernel(const __grid_constant__ Params
         p.episode[env] = p.episode[env] + 1u;
       }
     }
-    __syncwarp();
-    // observations of the new state (reference get_obs :232-316)
-    if (p.obs != nullptr) {
+    // observations of the new state (reference get_obs :232-316): a pure gather - the program maps
+    // every entry to a double inside this env's slab (or to a constant-zero slot for the padding)
+    if (p.obs != nullptr && valid) {
       double* o = p.obs + static_cast<size_t>(env) * ng * p.obs_dim;
       const int tot = ng * p.obs_dim;
-      auto busp = [&](int i) { return (i == 0) ? -P0 * p.base_mva : -s.a[A_PS][i] * p.base_mva; };
-      auto busq = [&](int i) { return (i == 0) ? -Q0 * p.base_mva : -s.a[A_QS][i] * p.base_mva; };
-      auto busvm = [&](int i) { return s.a[A_VM][i]; };
-      auto busva = [&](int i) { return s.a[A_VA][i]; };
-      auto sgp = [&](int j) { return s.pv[j]; };
-      auto sgq = [&](int j) { return s.q[j]; };
-      for (int idx = gl; idx < tot; idx += G) {
-        const int a = idx / p.obs_dim, k = idx - a * p.obs_dim;
-        const double v = obs_entry(p, a, k, busp, busq, busvm, busva, sgp, sgq);
-        if (valid) o[idx] = v;
-      }
+#pragma unroll 4
+      for (int idx = gl; idx < tot; idx += G) o[idx] = s.base[h.obs_off[idx]];
     }
     if (MODE == MODE_RESET && p.state != nullptr) {
       // get_state (:213-230): [P_bus | Q_bus | pv | q | vm | va(deg)]
       double* o = p.state + static_cast<size_t>(env) * p.state_dim;
       for (int idx = gl; idx < p.state_dim; idx += G) {
         double v;
-        if (idx < 2 * n) {
-          const int b = idx < n ? idx : idx - n;
-          const int i = __ldg(p.node_of_bus + b);
-          v = idx < n ? ((i == 0) ? -P0 * p.base_mva : -s.a[A_PS][i] * p.base_mva)
-                      : ((i == 0) ? -Q0 * p.base_mva : -s.a[A_QS][i] * p.base_mva);
-        } else if (idx < 2 * n + ng) v = s.pv[idx - 2 * n];
+        if (idx < n) v = BP[h.node_of_bus[idx]].x;
+        else if (idx < 2 * n) v = BP[h.node_of_bus[idx - n]].y;
+        else if (idx < 2 * n + ng) v = s.pv[idx - 2 * n];
         else if (idx < 2 * n + 2 * ng) v = s.q[idx - 2 * n - ng];
-        else if (idx < 3 * n + 2 * ng) v = s.a[A_VM][__ldg(p.node_of_bus + idx - 2 * n - 2 * ng)];
-        else v = s.a[A_VA][__ldg(p.node_of_bus + idx - 3 * n - 2 * ng)] * kRad2Deg;
+        else if (idx < 3 * n + 2 * ng) v = VV[h.node_of_bus[idx - 2 * n - 2 * ng]].x;
+        else v = VV[h.node_of_bus[idx - 3 * n - 2 * ng]].y * kRad2Deg;
         if (valid) o[idx] = v;
       }
     }

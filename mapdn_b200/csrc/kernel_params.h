@@ -4,40 +4,67 @@
 
 namespace mapdn {
 
-// doubles of per-env shared memory per node (see DESIGN.md "shared-memory layout")
-constexpr int kNodeArrays = 22;
-
-enum NodeArr {            // per-env, per-node arrays (index * n_pad)
-  A_VM = 0, A_VA, A_E, A_F, A_PS, A_QS, A_AUP, A_BUP, A_ADN, A_BDN,
-  A_D0, A_D1, A_D2, A_D3, A_R0, A_R1, A_S0, A_S1, A_S2, A_S3, A_T0, A_T1
+// Per-env shared memory: 9 double2 arrays of (npq + 1) entries (see DESIGN.md "shared-memory
+// layout"). Entry npq is a sentinel: the slack bus in VV / EF / SP, all-zero in UP / DN / T (the
+// "no child" slot of the branch-free child gathers).
+constexpr int kNodeArrays2 = 9;
+enum NodeArr2 {           // index of the double2 array inside an env slab
+  A_VV = 0,   // (|V|, theta)
+  A_EF,       // (e, f) = V in rectangular form
+  A_SP,       // (P_spec, Q_spec) p.u. injections (Sbus); slack slot: computed injection (P0, Q0)
+  A_UP,       // (a, b) of J[i, parent]      -> after elimination: S01 (first row of the Schur update)
+  A_DN,       // (a, b) of J[parent, i]      -> after elimination: S23
+  A_T,        // J[parent,i] D^-1 r  (rhs update for the parent)
+  A_D01,      // diagonal block row 0        -> after elimination: M01 = (D^-1 J[i,parent]) row 0
+  A_D23,      // diagonal block row 1        -> after elimination: M23
+  A_R         // rhs (-F)                    -> D^-1 r -> dx
 };
+// epilogue aliases (the Newton arrays are dead by then)
+constexpr int A_BP = A_D01;   // res_bus (p_mw, q_mvar) per node
+constexpr int A_OP = A_D23;   // "demand" columns of get_obs: res_bus p/q + sgen add-back (reference :238-244)
+constexpr uint32_t kNone = 0xFFFFu;   // "no parent" in 16-bit node fields
 
 struct HotLayout {        // byte offsets inside the hot static blob (staged into smem per CTA)
-  int gu, bu, gd, bd, gii, bii;        // double [n]: Y[i,parent], Y[parent,i], Y[i,i]
-  int parent, cstart, eorder, elev, dlev;  // uint16: [n], [n+1], [n-1], [n_elev+1], [n_dlev+1]
-  int bytes;                           // total, multiple of 16
+  int yup, ydn;           // double2 [npq]: Y[i,parent], Y[parent,i]   (G, B)
+  int yii, ysl;           // double2 [npq]: Y[i,i], Y[i,slack]
+  int ndesc;              // uint64 [npq]: parent | c0<<16 | c1<<32 | cextra_first<<48 ... see make_ndesc
+  int edesc;              // uint64 [npq]: same fields as ndesc[node] but ordered by elimination slot, + node
+  int enode;              // uint16 [npq]: node id of each elimination slot
+  int elev, dlev;         // uint16 [n_lev+1]: elimination-level / depth-level boundaries
+  int lptr, lidx;         // uint16 [npq+2], [n_load]: node -> loads (CSR); node npq = slack bus
+  int sptr, sidx;         // uint16 [npq+2], [n_sgen]: node -> sgens
+  int xptr, xidx;         // uint16 [npq+2], [<=n_sgen]: node -> sgens of the node's own zone (obs add-back)
+  int node_of_bus;        // uint16 [n_bus]: bus -> node (slack -> npq)
+  int obs_off;            // uint16 [n_sgen*obs_dim]: obs entry -> double offset inside the env slab
+  int bytes;              // total, multiple of 16
 };
 
+// node descriptor (64 bit): parent(16) | child0(16) | child1(16) | n_extra(8) | extra_first... packed as:
+//   bits  0-15 parent (kNone for roots)
+//   bits 16-31 first child  (npq = none -> zero slot)
+//   bits 32-47 second child (npq = none)
+//   bits 48-63 number of children beyond two (they follow child1 contiguously)
 struct Params {
   // ---- sizes ----
-  int n, n_pad, n_load, n_sgen, n_sgen_pad, n_line, n_elev, n_dlev, obs_dim, state_dim;
+  int n_bus, npq, n_load, n_sgen, n_line, n_lev, obs_dim, state_dim, n_slack_adj, slack_bus;
   int nb;                 // envs processed by this launch
-  int env_stride;         // doubles of smem per env
+  int env_stride2;        // double2 elements of smem per env
+  int pvq_off2;           // double2 offset of the sgen (pv | q | zero) block inside the env slab
   HotLayout hot_layout;
   const unsigned char* hot;
   // ---- cold static (global, read through the read-only path) ----
-  const int* bus_of_node; const int* node_of_bus;
-  const int* lptr; const int* lidx; const double* lscale;     // node -> loads (CSR)
-  const int* sptr; const int* sidx; const double* sscale;     // node -> sgens (CSR)
-  const int* line_f; const int* line_t; const double* line_c; // lines: nodes, 4 loss coefficients
-  const int* zptr; const int* znode;                          // agent -> zone bus slots (node ids)
-  const int* zsg_ptr; const int* zsg_idx;                     // zone slot -> sgens sitting on it
+  const int* bus_of_node;                                     // [npq]
+  const int* node_of_bus;                                     // [n_bus]; slack -> npq
+  const double* lscale; const double* sscale;                 // scaling by load id / sgen id
+  const int* line_f; const int* line_t; const double* line_c; // lines: node ids (npq = slack), 4 coefficients
+  const int* sl_node; const double* sl_y;                     // slack-adjacent nodes, Y[slack,i] (G,B)
+  const unsigned* obs_src; const int* obs_xptr; const int* obs_xidx;   // cold obs program of get_obs_kernel
   const double* s_max; const double* pv_std; const double* lp_std; const double* lq_std;
   // ---- profile store ----
   const double* prof_pv; const double* prof_lp; const double* prof_lq;
   long long n_rows; int steps_per_hour; int n_day_choices;
   // ---- scalars ----
-  double base_mva, inv_base, vm_init, e0, f0, vm0, va0, tol;
+  double base_mva, inv_base, vm_init, e0, f0, vm0, va0, ysl_g0, ysl_b0, tol;   // ysl_*0 = Y[slack,slack]
   int max_iter;
   int barrier; double voltage_weight, q_weight, line_weight; int use_line_weight;
   double v_upper, v_lower; int episode_limit; double action_low, action_high; int reset_action;
@@ -54,5 +81,8 @@ struct Params {
   int* out_iters; unsigned char* out_conv;
   double* reward; unsigned char* term; double* info; double* obs; double* state;
 };
+
+// cold obs program entry: kind in the top 4 bits, node / sgen index in the low 28
+enum ObsKind { OBS_ZERO = 0, OBS_P = 1, OBS_Q = 2, OBS_PV = 3, OBS_QSG = 4, OBS_VM = 5, OBS_VA = 6 };
 
 }  // namespace mapdn

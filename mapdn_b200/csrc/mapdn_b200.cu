@@ -87,21 +87,29 @@ __global__ void i64_to_double_kernel(long long n, const long long* __restrict__ 
   if (i < n) out[i] = static_cast<double>(in[i]);
 }
 
-// get_obs() from the state in HBM (reference :232-316)
+// get_obs() from the state in HBM (reference :232-316), driven by the precomputed obs program
 __global__ void get_obs_kernel(const __grid_constant__ Params p) {
   const int tot = p.n_sgen * p.obs_dim;
   const long long gid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (gid >= static_cast<long long>(p.nb) * tot) return;
   const int env = static_cast<int>(gid / tot), idx = static_cast<int>(gid - static_cast<long long>(env) * tot);
-  const int a = idx / p.obs_dim, k = idx - a * p.obs_dim;
-  const size_t eN = static_cast<size_t>(env) * p.n, eG = static_cast<size_t>(env) * p.n_sgen;
-  auto busp = [&](int i) { return p.res_p[eN + __ldg(p.bus_of_node + i)]; };
-  auto busq = [&](int i) { return p.res_q[eN + __ldg(p.bus_of_node + i)]; };
-  auto busvm = [&](int i) { return p.res_vm[eN + __ldg(p.bus_of_node + i)]; };
-  auto busva = [&](int i) { return p.res_va[eN + __ldg(p.bus_of_node + i)]; };
-  auto sgp = [&](int j) { return p.cur_pv[eG + j]; };
-  auto sgq = [&](int j) { return p.cur_q[eG + j]; };
-  p.obs[gid] = obs_entry(p, a, k, busp, busq, busvm, busva, sgp, sgq);
+  const size_t eN = static_cast<size_t>(env) * p.n_bus, eG = static_cast<size_t>(env) * p.n_sgen;
+  const unsigned src = __ldg(p.obs_src + idx);   // cold copy of the obs program (kind | node)
+  const int kind = static_cast<int>(src >> 28), ix = static_cast<int>(src & 0x0FFFFFFFu);
+  // node id -> bus id (npq = slack)
+  auto bus = [&](int i) { return (i == p.npq) ? p.slack_bus : __ldg(p.bus_of_node + i); };
+  double v = 0.0;
+  if (kind == OBS_P || kind == OBS_Q) {
+    v = (kind == OBS_P) ? p.res_p[eN + bus(ix)] : p.res_q[eN + bus(ix)];
+    for (int t = __ldg(p.obs_xptr + idx), te = __ldg(p.obs_xptr + idx + 1); t < te; ++t) {
+      const int sg = __ldg(p.obs_xidx + t);
+      v += (kind == OBS_P) ? p.cur_pv[eG + sg] : p.cur_q[eG + sg];
+    }
+  } else if (kind == OBS_PV) v = p.cur_pv[eG + ix];
+  else if (kind == OBS_QSG) v = p.cur_q[eG + ix];
+  else if (kind == OBS_VM) v = p.res_vm[eN + bus(ix)];
+  else if (kind == OBS_VA) v = p.res_va[eN + bus(ix)];
+  p.obs[gid] = v;
 }
 
 // get_state() (reference :213-230): [P_bus | Q_bus | pv | q | vm | va(deg)]
@@ -109,7 +117,7 @@ __global__ void get_state_kernel(const __grid_constant__ Params p) {
   const long long gid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (gid >= static_cast<long long>(p.nb) * p.state_dim) return;
   const int env = static_cast<int>(gid / p.state_dim), idx = static_cast<int>(gid - static_cast<long long>(env) * p.state_dim);
-  const int n = p.n, ng = p.n_sgen;
+  const int n = p.n_bus, ng = p.n_sgen;
   const size_t eN = static_cast<size_t>(env) * n, eG = static_cast<size_t>(env) * ng;
   double v;
   if (idx < n) v = p.res_p[eN + idx];
@@ -191,9 +199,11 @@ KernelFn kernel_for(int G, int mode) {
   }
 }
 
-int env_stride_for(int n, int ng, int G) {
-  int stride = kNodeArrays * n + 2 * ng;
-  while (stride % 16 != G % 16) ++stride;     // bank-conflict-free interleave of the envs of a warp
+// smem per env in double2 units: 9 arrays of (npq + 1) entries + sgen p/q. For G = 4 two envs share
+// a quarter-warp of a 128-bit access, so their slabs must start 64 B apart modulo 128 B.
+int env_stride2_for(int npq, int ng, int G) {
+  int stride = kNodeArrays2 * (npq + 1) + ng;
+  if (G == 4) while ((stride * 16) % 128 != 64) ++stride;
   return stride;
 }
 
@@ -296,7 +306,8 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     TRY_CUDA(cudaMemcpy(e->ydiag.data(), d_ydiag, e->ydiag.size() * sizeof(double), cudaMemcpyDeviceToHost));
   }
 
-  // ---- 2. symbolic analysis: merge parallel branches, BFS tree from the slack bus ----
+  // ---- 2. symbolic analysis: merge parallel branches, check the net is radial, build the forest
+  //         of PQ buses (slack removed) and re-root every tree at its centre ----
   struct Pair { double gab = 0, bab = 0, gba = 0, bba = 0; };   // Y[a,b], Y[b,a] with a < b
   std::map<std::pair<int, int>, Pair> pairs;
   for (int k = 0; k < nbr; ++k) {
@@ -307,102 +318,210 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     if (f < t) { pr.gab += y[2]; pr.bab += y[3]; pr.gba += y[4]; pr.bba += y[5]; }   // Ybus[f,t]+=Yft, [t,f]+=Ytf
     else       { pr.gba += y[2]; pr.bba += y[3]; pr.gab += y[4]; pr.bab += y[5]; }
   }
+  auto yoff = [&](int a, int b, double& g, double& bb) {          // Ybus[a,b]
+    const Pair& pr = pairs[{std::min(a, b), std::max(a, b)}];
+    if (a < b) { g = pr.gab; bb = pr.bab; } else { g = pr.gba; bb = pr.bba; }
+  };
+  const int slack = net->slack_bus;
   std::vector<std::vector<int>> adj(n);
   for (auto& kv : pairs) { adj[kv.first.first].push_back(kv.first.second); adj[kv.first.second].push_back(kv.first.first); }
   for (auto& a : adj) std::sort(a.begin(), a.end());
+  {   // connectivity + radiality on the full graph
+    std::vector<char> seen(n, 0);
+    std::vector<int> q{slack};
+    seen[slack] = 1;
+    for (size_t qh = 0; qh < q.size(); ++qh)
+      for (int v : adj[q[qh]]) if (!seen[v]) { seen[v] = 1; q.push_back(v); }
+    if (static_cast<int>(q.size()) != n)
+      return bail(fail(MAPDN_ERR_TOPOLOGY, "network is not connected to the slack bus (" +
+                                               std::to_string(n - q.size()) + " unreachable buses)"));
+    if (static_cast<int>(pairs.size()) != n - 1)
+      return bail(fail(MAPDN_ERR_TOPOLOGY, "network is meshed (" + std::to_string(pairs.size() - (n - 1)) +
+                                               " loop-closing branches); only radial feeders are supported"));
+  }
+  const int npq = n - 1;
+  // BFS inside the PQ forest (never crossing the slack bus)
+  auto bfs = [&](int src, std::vector<int>& dist, std::vector<int>& from) {
+    std::vector<int> q{src};
+    dist[src] = 0; from[src] = -1;
+    for (size_t qh = 0; qh < q.size(); ++qh)
+      for (int v : adj[q[qh]]) if (v != slack && dist[v] < 0) { dist[v] = dist[q[qh]] + 1; from[v] = q[qh]; q.push_back(v); }
+    return q;
+  };
+  std::vector<int> roots;
+  {
+    std::vector<int> d0(n, -1), f0(n, -1);
+    for (int s0 : adj[slack]) {                        // one tree per slack neighbour
+      if (d0[s0] >= 0) continue;
+      std::vector<int> comp = bfs(s0, d0, f0);
+      int u = comp.back();                             // farthest from s0
+      std::vector<int> d1(n, -1), f1(n, -1);
+      std::vector<int> c1 = bfs(u, d1, f1);
+      int v = c1.back();                               // farthest from u: u..v is a diameter
+      int c = v;
+      for (int k = 0; k < d1[v] / 2; ++k) c = f1[c];   // walk half-way back: the centre
+      roots.push_back(c);
+    }
+  }
   std::vector<int> order, node_of_bus(n, -1), parent_bus(n, -1), depth(n, 0);
-  order.reserve(n);
-  order.push_back(net->slack_bus);
-  node_of_bus[net->slack_bus] = 0;
-  size_t tree_edges = 0;
+  order.reserve(npq);
+  for (int r : roots) { node_of_bus[r] = static_cast<int>(order.size()); order.push_back(r); }
   for (size_t qh = 0; qh < order.size(); ++qh) {
     const int u = order[qh];
     for (int v : adj[u]) {
-      if (node_of_bus[v] >= 0) continue;
+      if (v == slack || node_of_bus[v] >= 0) continue;
       node_of_bus[v] = static_cast<int>(order.size());
       parent_bus[v] = u;
       depth[v] = depth[u] + 1;
       order.push_back(v);
-      ++tree_edges;
     }
   }
-  if (static_cast<int>(order.size()) != n)
-    return bail(fail(MAPDN_ERR_TOPOLOGY, "network is not connected to the slack bus (" +
-                                             std::to_string(n - order.size()) + " unreachable buses)"));
-  if (pairs.size() != tree_edges)
-    return bail(fail(MAPDN_ERR_TOPOLOGY, "network is meshed (" + std::to_string(pairs.size() - tree_edges) +
-                                             " loop-closing branches); only radial feeders are supported"));
-  std::vector<int> parent(n, 0), nchild(n, 0), height(n, 0);
-  for (int i = 1; i < n; ++i) { parent[i] = node_of_bus[parent_bus[order[i]]]; nchild[parent[i]]++; }
-  for (int i = n - 1; i >= 1; --i) height[parent[i]] = std::max(height[parent[i]], height[i] + 1);
-  std::vector<uint16_t> cstart(n + 1);
-  cstart[0] = 1;
-  for (int i = 0; i < n; ++i) cstart[i + 1] = static_cast<uint16_t>(cstart[i] + nchild[i]);
-  int max_h = 0, max_d = 0;
-  for (int i = 1; i < n; ++i) { max_h = std::max(max_h, height[i]); max_d = std::max(max_d, depth[order[i]]); }
-  const int n_elev = max_h + 1, n_dlev = max_d + 1;
-  std::vector<uint16_t> eorder, elev(n_elev + 1), dlev(n_dlev + 1);
+  node_of_bus[slack] = npq;
+  std::vector<int> parent(npq, -1), nchild(npq, 0), height(npq, 0);
+  for (int i = 0; i < npq; ++i)
+    if (parent_bus[order[i]] >= 0) { parent[i] = node_of_bus[parent_bus[order[i]]]; nchild[parent[i]]++; }
+  for (int i = npq - 1; i >= 0; --i)
+    if (parent[i] >= 0) height[parent[i]] = std::max(height[parent[i]], height[i] + 1);
+  std::vector<int> cfirst(npq + 1);
+  cfirst[0] = static_cast<int>(roots.size());
+  for (int i = 0; i < npq; ++i) cfirst[i + 1] = cfirst[i] + nchild[i];
+  int max_h = 0;
+  for (int i = 0; i < npq; ++i) max_h = std::max(max_h, height[i]);
+  const int n_lev = max_h + 1;                          // = max depth + 1
+  std::vector<uint16_t> elev(n_lev + 1), dlev(n_lev + 1);
+  std::vector<int> eorder;
   for (int hgt = 0; hgt <= max_h; ++hgt) {
     elev[hgt] = static_cast<uint16_t>(eorder.size());
-    for (int i = 1; i < n; ++i) if (height[i] == hgt) eorder.push_back(static_cast<uint16_t>(i));
+    for (int i = 0; i < npq; ++i) if (height[i] == hgt) eorder.push_back(i);
   }
-  elev[n_elev] = static_cast<uint16_t>(eorder.size());
+  elev[n_lev] = static_cast<uint16_t>(eorder.size());
   {
     int d = 0;
     dlev[0] = 0;
-    for (int i = 0; i < n; ++i) while (depth[order[i]] > d) dlev[++d] = static_cast<uint16_t>(i);
-    dlev[n_dlev] = static_cast<uint16_t>(n);
+    for (int i = 0; i < npq; ++i) while (depth[order[i]] > d) dlev[++d] = static_cast<uint16_t>(i);
+    while (d < n_lev) dlev[++d] = static_cast<uint16_t>(npq);
   }
   int max_width = 0;
-  for (int l = 0; l < n_elev; ++l) max_width = std::max(max_width, elev[l + 1] - elev[l]);
+  for (int l = 0; l < n_lev; ++l) max_width = std::max(max_width, elev[l + 1] - elev[l]);
 
-  // ---- 3. hot static blob ----
-  HotLayout hl{};
+  // ---- 3. element -> node maps (needed by the hot blob) ----
+  const int na = npq + 1;
+  if (2 * nl > 12 * na)
+    return bail(fail(MAPDN_ERR_UNSUPPORTED, "more than 6 loads per bus on average is not supported"));
+  std::vector<uint16_t> lptr(npq + 2, 0), lidx(std::max(1, nl)), sptr(npq + 2, 0), sidx(ng), xptr(npq + 2, 0), xidx;
   {
-    int off = 0;
-    auto take = [&](int bytes) { int o = off; off += (bytes + 15) / 16 * 16; return o; };
-    hl.gu = take(8 * n); hl.bu = take(8 * n); hl.gd = take(8 * n); hl.bd = take(8 * n);
-    hl.gii = take(8 * n); hl.bii = take(8 * n);
-    hl.parent = take(2 * n); hl.cstart = take(2 * (n + 1)); hl.eorder = take(2 * std::max(1, n - 1));
-    hl.elev = take(2 * (n_elev + 1)); hl.dlev = take(2 * (n_dlev + 1));
-    hl.bytes = off;
-  }
-  std::vector<unsigned char> hot(hl.bytes, 0);
-  {
-    double* gu = reinterpret_cast<double*>(hot.data() + hl.gu); double* bu = reinterpret_cast<double*>(hot.data() + hl.bu);
-    double* gd = reinterpret_cast<double*>(hot.data() + hl.gd); double* bd = reinterpret_cast<double*>(hot.data() + hl.bd);
-    double* gii = reinterpret_cast<double*>(hot.data() + hl.gii); double* bii = reinterpret_cast<double*>(hot.data() + hl.bii);
-    uint16_t* par = reinterpret_cast<uint16_t*>(hot.data() + hl.parent);
-    for (int i = 0; i < n; ++i) {
-      const int b = order[i];
-      gii[i] = e->ydiag[2 * b]; bii[i] = e->ydiag[2 * b + 1];
-      par[i] = static_cast<uint16_t>(parent[i]);
-      if (i == 0) continue;
-      const int pb = parent_bus[b];
-      const Pair& pr = pairs[{std::min(b, pb), std::max(b, pb)}];
-      if (b < pb) { gu[i] = pr.gab; bu[i] = pr.bab; gd[i] = pr.gba; bd[i] = pr.bba; }   // Y[i,parent], Y[parent,i]
-      else        { gu[i] = pr.gba; bu[i] = pr.bba; gd[i] = pr.gab; bd[i] = pr.bab; }
-    }
-    std::memcpy(hot.data() + hl.cstart, cstart.data(), 2 * (n + 1));
-    std::memcpy(hot.data() + hl.eorder, eorder.data(), 2 * eorder.size());
-    std::memcpy(hot.data() + hl.elev, elev.data(), 2 * elev.size());
-    std::memcpy(hot.data() + hl.dlev, dlev.data(), 2 * dlev.size());
-  }
-
-  // ---- 4. cold tables ----
-  std::vector<int> lptr(n + 1, 0), lidx(nl), sptr(n + 1, 0), sidx(ng);
-  {
-    std::vector<std::vector<int>> ln(n), sn(n);
+    std::vector<std::vector<int>> ln(npq + 1), sn(npq + 1);
     for (int l = 0; l < nl; ++l) ln[node_of_bus[net->load_bus[l]]].push_back(l);
     for (int j = 0; j < ng; ++j) sn[node_of_bus[net->sgen_bus[j]]].push_back(j);
     int a = 0, b = 0;
-    for (int i = 0; i < n; ++i) {
-      lptr[i] = a; sptr[i] = b;
-      for (int l : ln[i]) lidx[a++] = l;
-      for (int j : sn[i]) sidx[b++] = j;
+    for (int i = 0; i <= npq; ++i) {
+      lptr[i] = static_cast<uint16_t>(a); sptr[i] = static_cast<uint16_t>(b);
+      xptr[i] = static_cast<uint16_t>(xidx.size());
+      for (int l : ln[i]) lidx[a++] = static_cast<uint16_t>(l);
+      const int bus = (i == npq) ? slack : order[i];
+      for (int j : sn[i]) {
+        sidx[b++] = static_cast<uint16_t>(j);
+        if (net->sgen_zone[j] == net->bus_zone[bus]) xidx.push_back(static_cast<uint16_t>(j));   // reference :238-244
+      }
     }
-    lptr[n] = a; sptr[n] = b;
+    lptr[npq + 1] = static_cast<uint16_t>(a); sptr[npq + 1] = static_cast<uint16_t>(b);
+    xptr[npq + 1] = static_cast<uint16_t>(xidx.size());
   }
+  // obs program (reference get_obs :232-274): per agent [P_zone | Q_zone | pv | q | vm_zone | va_zone | 0...].
+  // Hot copy: double offset of the source inside the env slab. Cold copy (get_obs_kernel): kind | node.
+  int obs_dim = 0;
+  std::vector<std::vector<int>> zb(ng);
+  for (int a = 0; a < ng; ++a) {
+    for (int b = 0; b < n; ++b) if (net->bus_zone[b] == net->sgen_zone[a]) zb[a].push_back(b);
+    obs_dim = std::max(obs_dim, 4 * static_cast<int>(zb[a].size()) + 2);
+  }
+  const int pvq_off2 = kNodeArrays2 * na;
+  if (2 * (pvq_off2 + ng) >= 65535)
+    return bail(fail(MAPDN_ERR_UNSUPPORTED, "network too large for 16-bit slab offsets"));
+  std::vector<uint16_t> obs_off(static_cast<size_t>(ng) * obs_dim);
+  std::vector<unsigned> obs_src(static_cast<size_t>(ng) * obs_dim, 0u);
+  std::vector<int> obs_xptr(static_cast<size_t>(ng) * obs_dim + 1, 0), obs_xidx;
+  enum { K_ZERO = 0, K_P = 1, K_Q = 2, K_PV = 3, K_QSG = 4, K_VM = 5, K_VA = 6 };
+  for (int a = 0; a < ng; ++a) {
+    const int nz = static_cast<int>(zb[a].size());
+    for (int k = 0; k < obs_dim; ++k) {
+      const size_t idx = static_cast<size_t>(a) * obs_dim + k;
+      obs_xptr[idx] = static_cast<int>(obs_xidx.size());
+      unsigned kind = K_ZERO, ix = 0;
+      int off = 2 * (A_UP * na + npq);                         // UP[npq].x: constant zero
+      if (k < 2 * nz) {
+        const int b = zb[a][k % nz];
+        kind = (k < nz) ? K_P : K_Q; ix = static_cast<unsigned>(node_of_bus[b]);
+        off = 2 * (A_OP * na + node_of_bus[b]) + (k < nz ? 0 : 1);
+        for (int j = 0; j < ng; ++j)
+          if (net->sgen_zone[j] == net->sgen_zone[a] && net->sgen_bus[j] == b) obs_xidx.push_back(j);
+      } else if (k == 2 * nz) { kind = K_PV; ix = static_cast<unsigned>(a); off = 2 * pvq_off2 + a; }
+      else if (k == 2 * nz + 1) { kind = K_QSG; ix = static_cast<unsigned>(a); off = 2 * pvq_off2 + ng + a; }
+      else if (k < 3 * nz + 2) { const int i = node_of_bus[zb[a][k - 2 * nz - 2]]; kind = K_VM; ix = i; off = 2 * (A_VV * na + i); }
+      else if (k < 4 * nz + 2) { const int i = node_of_bus[zb[a][k - 3 * nz - 2]]; kind = K_VA; ix = i; off = 2 * (A_VV * na + i) + 1; }
+      obs_src[idx] = (kind << 28) | ix;
+      obs_off[idx] = static_cast<uint16_t>(off);
+    }
+  }
+  obs_xptr[static_cast<size_t>(ng) * obs_dim] = static_cast<int>(obs_xidx.size());
+
+  // ---- 3b. hot static blob ----
+  HotLayout hl{};
+  {
+    int off = 0;
+    auto take = [&](size_t bytes) { int o = off; off += static_cast<int>((bytes + 15) / 16 * 16); return o; };
+    hl.yup = take(16 * npq); hl.ydn = take(16 * npq); hl.yii = take(16 * npq); hl.ysl = take(16 * npq);
+    hl.ndesc = take(8 * npq); hl.edesc = take(8 * npq); hl.enode = take(2 * npq);
+    hl.elev = take(2 * (n_lev + 1)); hl.dlev = take(2 * (n_lev + 1));
+    hl.lptr = take(2 * lptr.size()); hl.lidx = take(2 * lidx.size());
+    hl.sptr = take(2 * sptr.size()); hl.sidx = take(2 * sidx.size());
+    hl.xptr = take(2 * xptr.size()); hl.xidx = take(2 * std::max<size_t>(1, xidx.size()));
+    hl.node_of_bus = take(2 * n); hl.obs_off = take(2 * obs_off.size());
+    hl.bytes = off;
+  }
+  std::vector<unsigned char> hot(hl.bytes, 0);
+  std::vector<int> sl_node;
+  std::vector<double> sl_y;
+  {
+    double* yup = reinterpret_cast<double*>(hot.data() + hl.yup); double* ydn = reinterpret_cast<double*>(hot.data() + hl.ydn);
+    double* yii = reinterpret_cast<double*>(hot.data() + hl.yii); double* ysl = reinterpret_cast<double*>(hot.data() + hl.ysl);
+    uint64_t* ndesc = reinterpret_cast<uint64_t*>(hot.data() + hl.ndesc);
+    uint64_t* edesc = reinterpret_cast<uint64_t*>(hot.data() + hl.edesc);
+    uint16_t* enode = reinterpret_cast<uint16_t*>(hot.data() + hl.enode);
+    for (int i = 0; i < npq; ++i) {
+      const int b = order[i];
+      yii[2 * i] = e->ydiag[2 * b]; yii[2 * i + 1] = e->ydiag[2 * b + 1];
+      if (parent[i] >= 0) {
+        yoff(b, parent_bus[b], yup[2 * i], yup[2 * i + 1]);       // Y[i,parent]
+        yoff(parent_bus[b], b, ydn[2 * i], ydn[2 * i + 1]);       // Y[parent,i]
+      }
+      if (pairs.count({std::min(b, slack), std::max(b, slack)})) {
+        yoff(b, slack, ysl[2 * i], ysl[2 * i + 1]);               // Y[i,slack]
+        double g, bb;
+        yoff(slack, b, g, bb);                                     // Y[slack,i]
+        sl_node.push_back(i); sl_y.push_back(g); sl_y.push_back(bb);
+      }
+      // parent | child0 | child1 | number of further children (contiguous after child1); npq = zero slot
+      const uint64_t pa = parent[i] >= 0 ? static_cast<uint64_t>(parent[i]) : kNone;
+      const uint64_t c0 = nchild[i] > 0 ? cfirst[i] : npq, c1 = nchild[i] > 1 ? cfirst[i] + 1 : npq;
+      const uint64_t nx = nchild[i] > 2 ? nchild[i] - 2 : 0;
+      ndesc[i] = pa | (c0 << 16) | (c1 << 32) | (nx << 48);
+    }
+    for (int k = 0; k < npq; ++k) { enode[k] = static_cast<uint16_t>(eorder[k]); edesc[k] = ndesc[eorder[k]]; }
+    std::memcpy(hot.data() + hl.elev, elev.data(), 2 * elev.size());
+    std::memcpy(hot.data() + hl.dlev, dlev.data(), 2 * dlev.size());
+    std::memcpy(hot.data() + hl.lptr, lptr.data(), 2 * lptr.size());
+    if (nl) std::memcpy(hot.data() + hl.lidx, lidx.data(), 2 * static_cast<size_t>(nl));
+    std::memcpy(hot.data() + hl.sptr, sptr.data(), 2 * sptr.size());
+    std::memcpy(hot.data() + hl.sidx, sidx.data(), 2 * sidx.size());
+    std::memcpy(hot.data() + hl.xptr, xptr.data(), 2 * xptr.size());
+    if (!xidx.empty()) std::memcpy(hot.data() + hl.xidx, xidx.data(), 2 * xidx.size());
+    uint16_t* nob = reinterpret_cast<uint16_t*>(hot.data() + hl.node_of_bus);
+    for (int b = 0; b < n; ++b) nob[b] = static_cast<uint16_t>(node_of_bus[b]);
+    std::memcpy(hot.data() + hl.obs_off, obs_off.data(), 2 * obs_off.size());
+  }
+
+  // ---- 4. cold tables ----
   std::vector<double> lscale = vec_or(net->load_scaling, nl, 1.0), sscale = vec_or(net->sgen_scaling, ng, 1.0);
   std::vector<int> line_f, line_t;
   std::vector<double> line_c;
@@ -416,32 +535,18 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     line_c.push_back((y[2] + y[4]) * net->base_mva); line_c.push_back((y[3] - y[5]) * net->base_mva);
   }
   const int n_line = static_cast<int>(line_f.size());
-  std::vector<int> zptr(ng + 1, 0), znode, zsg_ptr, zsg_idx;
-  int obs_dim = 0;
-  for (int a = 0; a < ng; ++a) {
-    zptr[a] = static_cast<int>(znode.size());
-    for (int b = 0; b < n; ++b) {
-      if (net->bus_zone[b] != net->sgen_zone[a]) continue;
-      zsg_ptr.push_back(static_cast<int>(zsg_idx.size()));
-      for (int j = 0; j < ng; ++j)
-        if (net->sgen_zone[j] == net->sgen_zone[a] && net->sgen_bus[j] == b) zsg_idx.push_back(j);
-      znode.push_back(node_of_bus[b]);
-    }
-    const int nz = static_cast<int>(znode.size()) - zptr[a];
-    obs_dim = std::max(obs_dim, 4 * nz + 2);
-  }
-  zptr[ng] = static_cast<int>(znode.size());
-  zsg_ptr.push_back(static_cast<int>(zsg_idx.size()));
 
   // ---- 5. launch geometry ----
   cudaDeviceProp dp{};
   TRY_CUDA(cudaGetDeviceProperties(&dp, device));
   int G = cfg->lanes_per_env;
-  if (G == 0) G = (n <= 96) ? 8 : (n <= 200 ? 16 : 32);
-  const int stride = env_stride_for(n, ng, G);
+  if (G == 0) G = (npq <= 96) ? 8 : (npq <= 200 ? 16 : 32);
+  const int stride2 = env_stride2_for(npq, ng, G);
   const size_t max_smem = dp.sharedMemPerBlockOptin;
+  auto smem_for = [&](int w) { return static_cast<size_t>(hl.bytes) + static_cast<size_t>(w) * (32 / G) * stride2 * 16; };
   int warps = 4;
-  auto smem_for = [&](int w) { return static_cast<size_t>(hl.bytes) + static_cast<size_t>(w) * (32 / G) * stride * 8; };
+  // prefer enough CTAs to spread over all SMs
+  while (warps > 1 && (cfg->batch + warps * (32 / G) - 1) / (warps * (32 / G)) < 2 * dp.multiProcessorCount) warps /= 2;
   while (warps > 1 && smem_for(warps) > max_smem) --warps;
   if (smem_for(warps) > max_smem)
     return bail(fail(MAPDN_ERR_UNSUPPORTED, "network too large for the shared-memory resident solver (" +
@@ -459,17 +564,17 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
 
   // ---- 6. upload + env state ----
   Params& P = e->base;
-  P.n = n; P.n_pad = n; P.n_load = nl; P.n_sgen = ng; P.n_sgen_pad = ng; P.n_line = n_line;
-  P.n_elev = n_elev; P.n_dlev = n_dlev; P.obs_dim = obs_dim; P.state_dim = 4 * n + 2 * ng;
-  P.nb = cfg->batch; P.env_stride = stride; P.hot_layout = hl;
+  P.n_bus = n; P.npq = npq; P.n_load = nl; P.n_sgen = ng; P.n_line = n_line; P.n_lev = n_lev;
+  P.obs_dim = obs_dim; P.state_dim = 4 * n + 2 * ng; P.n_slack_adj = static_cast<int>(sl_node.size());
+  P.slack_bus = slack;
+  P.nb = cfg->batch; P.env_stride2 = stride2; P.pvq_off2 = pvq_off2; P.hot_layout = hl;
   std::vector<int> bus_of_node(order.begin(), order.end());
   TRY(dev_upload(e, hot, &P.hot));
   TRY(dev_upload(e, bus_of_node, &P.bus_of_node)); TRY(dev_upload(e, node_of_bus, &P.node_of_bus));
-  TRY(dev_upload(e, lptr, &P.lptr)); TRY(dev_upload(e, lidx, &P.lidx)); TRY(dev_upload(e, lscale, &P.lscale));
-  TRY(dev_upload(e, sptr, &P.sptr)); TRY(dev_upload(e, sidx, &P.sidx)); TRY(dev_upload(e, sscale, &P.sscale));
+  TRY(dev_upload(e, lscale, &P.lscale)); TRY(dev_upload(e, sscale, &P.sscale));
   TRY(dev_upload(e, line_f, &P.line_f)); TRY(dev_upload(e, line_t, &P.line_t)); TRY(dev_upload(e, line_c, &P.line_c));
-  TRY(dev_upload(e, zptr, &P.zptr)); TRY(dev_upload(e, znode, &P.znode));
-  TRY(dev_upload(e, zsg_ptr, &P.zsg_ptr)); TRY(dev_upload(e, zsg_idx, &P.zsg_idx));
+  TRY(dev_upload(e, sl_node, &P.sl_node)); TRY(dev_upload(e, sl_y, &P.sl_y));
+  TRY(dev_upload(e, obs_src, &P.obs_src)); TRY(dev_upload(e, obs_xptr, &P.obs_xptr)); TRY(dev_upload(e, obs_xidx, &P.obs_xidx));
   const size_t B = static_cast<size_t>(cfg->batch);
   if (prof) {
     const size_t T = static_cast<size_t>(prof->n_rows);
@@ -498,6 +603,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   P.vm_init = (net->vm_init > 0) ? net->vm_init : net->slack_vm;
   P.vm0 = net->slack_vm; P.va0 = net->slack_va_deg * (3.14159265358979323846 / 180.0);
   P.e0 = P.vm0 * std::cos(P.va0); P.f0 = P.vm0 * std::sin(P.va0);
+  P.ysl_g0 = e->ydiag[2 * slack]; P.ysl_b0 = e->ydiag[2 * slack + 1];
   P.tol = (cfg->tol > 0) ? cfg->tol : 1e-8;
   P.max_iter = (cfg->max_iter > 0) ? cfg->max_iter : 10;
   P.barrier = cfg->barrier; P.voltage_weight = cfg->voltage_weight; P.q_weight = cfg->q_weight;
@@ -519,7 +625,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   mapdn_dims& d = e->dims;
   d.batch = cfg->batch; d.n_bus = n; d.n_branch = nbr; d.n_line = n_line; d.n_load = nl; d.n_sgen = ng;
   d.n_agents = ng; d.n_actions = 1; d.obs_dim = obs_dim; d.state_dim = P.state_dim; d.n_info = MAPDN_N_INFO;
-  d.lanes_per_env = G; d.envs_per_block = e->epb; d.smem_bytes = e->smem; d.n_levels = n_elev;
+  d.lanes_per_env = G; d.envs_per_block = e->epb; d.smem_bytes = e->smem; d.n_levels = n_lev;
   // read p_load,q_load,p_pv,a ; write vm,va ; write obs ; reward+done+11 info
   d.algorithmic_bytes_per_env_step = 8LL * (2 * nl + 2 * ng) + 8LL * 2 * n + 8LL * ng * obs_dim + 8LL * 13;
   (void)max_width;
@@ -610,10 +716,10 @@ mapdn_status mapdn_get_field(mapdn_env* e, int32_t field, double* out_dev, void*
   long long cnt = 0;
   double scale = 1.0;
   switch (field) {
-    case MAPDN_FIELD_VM: src = p.res_vm; cnt = B * p.n; break;
-    case MAPDN_FIELD_VA_DEG: src = p.res_va; cnt = B * p.n; scale = 57.295779513082320876798; break;
-    case MAPDN_FIELD_P_BUS: src = p.res_p; cnt = B * p.n; break;
-    case MAPDN_FIELD_Q_BUS: src = p.res_q; cnt = B * p.n; break;
+    case MAPDN_FIELD_VM: src = p.res_vm; cnt = B * p.n_bus; break;
+    case MAPDN_FIELD_VA_DEG: src = p.res_va; cnt = B * p.n_bus; scale = 57.295779513082320876798; break;
+    case MAPDN_FIELD_P_BUS: src = p.res_p; cnt = B * p.n_bus; break;
+    case MAPDN_FIELD_Q_BUS: src = p.res_q; cnt = B * p.n_bus; break;
     case MAPDN_FIELD_P_SGEN: src = p.cur_pv; cnt = B * p.n_sgen; break;
     case MAPDN_FIELD_Q_SGEN: src = p.cur_q; cnt = B * p.n_sgen; break;
     case MAPDN_FIELD_LINE_LOSS: src = p.res_pl; cnt = B * p.n_line; break;

@@ -36,12 +36,22 @@ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
 
 struct RngKey { uint32_t k0, k1, env, c3base; };   // c3base = episode * 8
 
-// |N(0,1)| for profile element `elem` drawn at counter c1 (= steps, or kResetFlag|attempt).
-// Box-Muller, cosine branch (reference: np.abs(np.random.randn()), :498,503,508).
-__device__ __forceinline__ double half_normal(const RngKey& k, uint32_t c1, uint32_t elem) {
-  const u32x4 r = philox4x32_10(elem, c1, k.env, k.c3base + kStreamNoise, k.k0, k.k1);
+// |N(0,1)| noise of the profile rows (reference: np.abs(np.random.randn()), :498,503,508).
+// One Philox call yields the Box-Muller pair of elements (2m, 2m+1): |r cos(2 pi u2)|, |r sin(2 pi u2)|,
+// drawn at counter c1 (= steps, or kResetFlag|attempt).
+__device__ __forceinline__ void half_normal_pair(const RngKey& k, uint32_t c1, uint32_t pair, double& z0, double& z1) {
+  const u32x4 r = philox4x32_10(pair, c1, k.env, k.c3base + kStreamNoise, k.k0, k.k1);
   const double u1 = u53(r.x, r.y), u2 = u53(r.z, r.w);
-  return fabs(sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925 * u2));
+  const double rad = sqrt(-2.0 * log(u1));
+  double sn, cs;
+  sincos(6.283185307179586476925 * u2, &sn, &cs);
+  z0 = fabs(rad * cs);
+  z1 = fabs(rad * sn);
+}
+__device__ __forceinline__ double half_normal(const RngKey& k, uint32_t c1, uint32_t elem) {
+  double z0, z1;
+  half_normal_pair(k, c1, elem >> 1, z0, z1);
+  return (elem & 1u) ? z1 : z0;
 }
 
 }  // namespace mapdn

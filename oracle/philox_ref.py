@@ -45,12 +45,15 @@ def _c3(episode, stream):
 
 
 def half_normal(seed, env, episode, c1, elems):
-    """|N(0,1)| for element indices ``elems`` (Box-Muller, cosine branch)."""
+    """|N(0,1)| for element indices ``elems``: elements (2m, 2m+1) share one Philox call (Box-Muller pair:
+    cosine branch for the even element, sine branch for the odd one)."""
     elems = np.asarray(elems, np.uint64)
-    x0, x1, x2, x3 = philox4x32_10(elems, np.uint64(c1), np.uint64(env), np.uint64(_c3(episode, STREAM_NOISE)),
-                                   seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    x0, x1, x2, x3 = philox4x32_10(elems >> np.uint64(1), np.uint64(c1), np.uint64(env),
+                                   np.uint64(_c3(episode, STREAM_NOISE)), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     u1, u2 = _u53(x0, x1), _u53(x2, x3)
-    return np.abs(np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2))
+    rad = np.sqrt(-2.0 * np.log(u1))
+    ang = 2.0 * np.pi * u2
+    return np.abs(rad * np.where((elems & np.uint64(1)) == 1, np.sin(ang), np.cos(ang)))
 
 
 def start_time(seed, env, episode, attempt, n_day_choices, steps_per_hour):
