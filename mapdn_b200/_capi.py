@@ -15,7 +15,7 @@ import numpy as np
 from .network import NetDesc, ProfileDesc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmapdn_b200.so")
+LIB_PATH = os.environ.get("MAPDN_B200_LIB") or os.path.join(_HERE, "libmapdn_b200.so")   # env override: kernel experiments
 
 BARRIERS = {"l1": 0, "l2": 1, "bowl": 2, "bump": 3, "courant_beltrami": 4}
 INFO_KEYS = ("percentage_of_v_out_of_control", "percentage_of_lower_than_lower_v",

@@ -36,7 +36,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + SOURCES
+    extra = ["-DMAPDN_PROFILE"] if os.environ.get("MAPDN_PROFILE_BUILD") else []
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB] + SOURCES
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -4,11 +4,14 @@
 
 namespace mapdn {
 
-// Per-env shared memory: 9 double2 arrays of (npq + 1) entries (see DESIGN.md "shared-memory
-// layout"). Entry npq is a sentinel: the slack bus in VV / EF / SP, all-zero in UP / DN / T (the
-// "no child" slot of the branch-free child gathers).
+// Per-env shared memory: (npq + 2) node records of 9 double2 (144 B, array-of-structs: one address
+// computation per node, 128-bit accesses; consecutive nodes are bank-conflict free), then the sgen
+// block (pv | q), then a scratch region of ng + 2 n_load doubles (DESIGN.md "shared-memory layout").
+// Record npq is a sentinel: the slack bus in VV / EF / SP, all-zero in UP / DN / T / R (the "no child" /
+// "no parent" slot of the branch-free gathers). Record npq + 1 is a trash record: idle lanes of a
+// schedule step work on it so that the level sweeps have no divergent branches.
 constexpr int kNodeArrays2 = 9;
-enum NodeArr2 {           // index of the double2 array inside an env slab
+enum NodeArr2 {           // index of the double2 field inside a node record
   A_VV = 0,   // (|V|, theta)
   A_EF,       // (e, f) = V in rectangular form
   A_SP,       // (P_spec, Q_spec) p.u. injections (Sbus); slack slot: computed injection (P0, Q0)
@@ -28,14 +31,16 @@ struct HotLayout {        // byte offsets inside the hot static blob (staged int
   int yup, ydn;           // double2 [npq]: Y[i,parent], Y[parent,i]   (G, B)
   int yii, ysl;           // double2 [npq]: Y[i,i], Y[i,slack]
   int ndesc;              // uint64 [npq]: parent | c0<<16 | c1<<32 | cextra_first<<48 ... see make_ndesc
-  int edesc;              // uint64 [npq]: same fields as ndesc[node] but ordered by elimination slot, + node
-  int enode;              // uint16 [npq]: node id of each elimination slot
-  int elev, dlev;         // uint16 [n_lev+1]: elimination-level / depth-level boundaries
+  int esched;             // uint64 [n_esteps * G]: elimination schedule, one entry per (step, lane):
+                          //   node | child0<<16 | child1<<32 | n_extra_children<<48   (idle lane: trash record)
+  int bsched;             // uint32 [n_bsteps * G]: back-substitution schedule: node | parent<<16
   int lptr, lidx;         // uint16 [npq+2], [n_load]: node -> loads (CSR); node npq = slack bus
   int sptr, sidx;         // uint16 [npq+2], [n_sgen]: node -> sgens
   int xptr, xidx;         // uint16 [npq+2], [<=n_sgen]: node -> sgens of the node's own zone (obs add-back)
   int node_of_bus;        // uint16 [n_bus]: bus -> node (slack -> npq)
   int obs_off;            // uint16 [n_sgen*obs_dim]: obs entry -> double offset inside the env slab
+  int line_nodes;         // uint16 [2*n_line]: from / to node of every line (npq = slack)
+  int line_c;             // double [4*n_line]: loss coefficients (see mapdn_b200.cu)
   int bytes;              // total, multiple of 16
 };
 
@@ -47,16 +52,17 @@ struct HotLayout {        // byte offsets inside the hot static blob (staged int
 struct Params {
   // ---- sizes ----
   int n_bus, npq, n_load, n_sgen, n_line, n_lev, obs_dim, state_dim, n_slack_adj, slack_bus;
+  int n_esteps, n_bsteps, has_extra_children;   // schedule lengths (for the handle's G); any bus with > 2 children
   int nb;                 // envs processed by this launch
   int env_stride2;        // double2 elements of smem per env
-  int pvq_off2;           // double2 offset of the sgen (pv | q | zero) block inside the env slab
+  int pvq_off2;           // double2 offset of the sgen (pv | q) block inside the env slab
+  int scratch_off2;       // double2 offset of the scratch region (prologue staging / next-row prefetch)
   HotLayout hot_layout;
   const unsigned char* hot;
   // ---- cold static (global, read through the read-only path) ----
   const int* bus_of_node;                                     // [npq]
   const int* node_of_bus;                                     // [n_bus]; slack -> npq
   const double* lscale; const double* sscale;                 // scaling by load id / sgen id
-  const int* line_f; const int* line_t; const double* line_c; // lines: node ids (npq = slack), 4 coefficients
   const int* sl_node; const double* sl_y;                     // slack-adjacent nodes, Y[slack,i] (G,B)
   const unsigned* obs_src; const int* obs_xptr; const int* obs_xidx;   // cold obs program of get_obs_kernel
   const double* s_max; const double* pv_std; const double* lp_std; const double* lq_std;
@@ -80,6 +86,7 @@ struct Params {
   double* out_vm; double* out_va; double* out_p; double* out_q; double* out_pl;
   int* out_iters; unsigned char* out_conv;
   double* reward; unsigned char* term; double* info; double* obs; double* state;
+  long long* prof;        // MAPDN_PROFILE builds: per-phase clock64 totals of warp 0 of block 0
 };
 
 // cold obs program entry: kind in the top 4 bits, node / sgen index in the low 28

@@ -199,10 +199,11 @@ KernelFn kernel_for(int G, int mode) {
   }
 }
 
-// smem per env in double2 units: 9 arrays of (npq + 1) entries + sgen p/q. For G = 4 two envs share
-// a quarter-warp of a 128-bit access, so their slabs must start 64 B apart modulo 128 B.
-int env_stride2_for(int npq, int ng, int G) {
-  int stride = kNodeArrays2 * (npq + 1) + ng;
+// smem per env in double2 units: (npq + 1) node records of 9 double2, sgen p/q, scratch of ng + 2 nl
+// doubles. For G = 4 two envs share a quarter-warp of a 128-bit access, so their slabs must start
+// 64 B apart modulo 128 B.
+int env_stride2_for(int npq, int ng, int nl, int G) {
+  int stride = kNodeArrays2 * (npq + 2) + ng + (ng + 2 * nl + 1) / 2;
   if (G == 4) while ((stride * 16) % 128 != 64) ++stride;
   return stride;
 }
@@ -213,9 +214,29 @@ mapdn_status launch_env_kernel(mapdn_env* e, int mode, Params& p, cudaStream_t s
   int grid = std::min(needed, std::max(1, e->max_blocks));
   const int rounds = (needed + grid - 1) / grid;
   grid = (needed + rounds - 1) / rounds;       // balance the persistent loop
+#ifdef MAPDN_PROFILE
+  static long long* d_prof = nullptr;
+  if (!d_prof) cudaMalloc(&d_prof, 12 * sizeof(long long));
+  cudaMemset(d_prof, 0, 12 * sizeof(long long));
+  p.prof = d_prof;
+#endif
   fn<<<grid, e->threads, e->smem, st>>>(p);
   MAPDN_CUDA(cudaGetLastError());
   e->launches++;
+#ifdef MAPDN_PROFILE
+  {
+    long long hp[12];
+    cudaDeviceSynchronize();
+    cudaMemcpy(hp, d_prof, sizeof(hp), cudaMemcpyDeviceToHost);
+    static const char* nm[12] = {"-", "setup+prologue", "init/update", "edges", "F/diag", "elim", "backsub", "reload+slack",
+                                 "q+nextrow", "BP/OP+bus+lines", "reward/info", "obs/state"};
+    long long tot = 0;
+    for (int k = 0; k < 12; ++k) tot += hp[k];
+    fprintf(stderr, "[prof mode=%d nb=%d] total %lld cyc:", mode, p.nb, tot);
+    for (int k = 1; k < 12; ++k) fprintf(stderr, " %s=%lld", nm[k], hp[k]);
+    fprintf(stderr, "\n");
+  }
+#endif
   return MAPDN_OK;
 }
 
@@ -401,13 +422,34 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     for (int i = 0; i < npq; ++i) while (depth[order[i]] > d) dlev[++d] = static_cast<uint16_t>(i);
     while (d < n_lev) dlev[++d] = static_cast<uint16_t>(npq);
   }
-  int max_width = 0;
+  int max_width = 0, max_children = 0;
   for (int l = 0; l < n_lev; ++l) max_width = std::max(max_width, elev[l + 1] - elev[l]);
+  for (int i = 0; i < npq; ++i) max_children = std::max(max_children, nchild[i]);
+  int G = cfg->lanes_per_env;
+  if (G == 0) G = (npq <= 96) ? 8 : (npq <= 200 ? 16 : 32);
+  // flat schedules for this G: a level wider than G takes several steps; idle lanes get the trash record
+  const int trash = npq + 1;
+  std::vector<uint64_t> esched;
+  std::vector<uint32_t> bsched;
+  auto edesc_of = [&](int i) {
+    const uint64_t c0 = nchild[i] > 0 ? cfirst[i] : npq, c1 = nchild[i] > 1 ? cfirst[i] + 1 : npq;
+    const uint64_t nx = nchild[i] > 2 ? nchild[i] - 2 : 0;
+    return static_cast<uint64_t>(i) | (c0 << 16) | (c1 << 32) | (nx << 48);
+  };
+  const uint64_t e_idle = static_cast<uint64_t>(trash) | (static_cast<uint64_t>(npq) << 16) | (static_cast<uint64_t>(npq) << 32);
+  for (int l = 0; l < n_lev; ++l)
+    for (int b0 = elev[l]; b0 < elev[l + 1]; b0 += G)
+      for (int g = 0; g < G; ++g) esched.push_back(b0 + g < elev[l + 1] ? edesc_of(eorder[b0 + g]) : e_idle);
+  const uint32_t b_idle = static_cast<uint32_t>(trash) | (static_cast<uint32_t>(npq) << 16);
+  for (int l = 1; l < n_lev; ++l)
+    for (int b0 = dlev[l]; b0 < dlev[l + 1]; b0 += G)
+      for (int g = 0; g < G; ++g)
+        bsched.push_back(b0 + g < dlev[l + 1] ? (static_cast<uint32_t>(b0 + g) | (static_cast<uint32_t>(parent[b0 + g]) << 16)) : b_idle);
+  const int n_esteps = static_cast<int>(esched.size()) / G, n_bsteps = static_cast<int>(bsched.size()) / G;
+  if (bsched.empty()) bsched.assign(G, b_idle);
 
   // ---- 3. element -> node maps (needed by the hot blob) ----
-  const int na = npq + 1;
-  if (2 * nl > 12 * na)
-    return bail(fail(MAPDN_ERR_UNSUPPORTED, "more than 6 loads per bus on average is not supported"));
+  const int na = npq + 2;      // + sentinel + trash records
   std::vector<uint16_t> lptr(npq + 2, 0), lidx(std::max(1, nl)), sptr(npq + 2, 0), sidx(ng), xptr(npq + 2, 0), xidx;
   {
     std::vector<std::vector<int>> ln(npq + 1), sn(npq + 1);
@@ -435,8 +477,8 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     for (int b = 0; b < n; ++b) if (net->bus_zone[b] == net->sgen_zone[a]) zb[a].push_back(b);
     obs_dim = std::max(obs_dim, 4 * static_cast<int>(zb[a].size()) + 2);
   }
-  const int pvq_off2 = kNodeArrays2 * na;
-  if (2 * (pvq_off2 + ng) >= 65535)
+  const int pvq_off2 = kNodeArrays2 * na, scratch_off2 = pvq_off2 + ng;
+  if (2 * (scratch_off2 + (ng + 2 * nl + 1) / 2) >= 65535)
     return bail(fail(MAPDN_ERR_UNSUPPORTED, "network too large for 16-bit slab offsets"));
   std::vector<uint16_t> obs_off(static_cast<size_t>(ng) * obs_dim);
   std::vector<unsigned> obs_src(static_cast<size_t>(ng) * obs_dim, 0u);
@@ -448,22 +490,37 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
       const size_t idx = static_cast<size_t>(a) * obs_dim + k;
       obs_xptr[idx] = static_cast<int>(obs_xidx.size());
       unsigned kind = K_ZERO, ix = 0;
-      int off = 2 * (A_UP * na + npq);                         // UP[npq].x: constant zero
+      int off = 2 * (npq * kNodeArrays2 + A_UP);               // sentinel record's UP.x: constant zero
       if (k < 2 * nz) {
         const int b = zb[a][k % nz];
         kind = (k < nz) ? K_P : K_Q; ix = static_cast<unsigned>(node_of_bus[b]);
-        off = 2 * (A_OP * na + node_of_bus[b]) + (k < nz ? 0 : 1);
+        off = 2 * (node_of_bus[b] * kNodeArrays2 + A_OP) + (k < nz ? 0 : 1);
         for (int j = 0; j < ng; ++j)
           if (net->sgen_zone[j] == net->sgen_zone[a] && net->sgen_bus[j] == b) obs_xidx.push_back(j);
       } else if (k == 2 * nz) { kind = K_PV; ix = static_cast<unsigned>(a); off = 2 * pvq_off2 + a; }
       else if (k == 2 * nz + 1) { kind = K_QSG; ix = static_cast<unsigned>(a); off = 2 * pvq_off2 + ng + a; }
-      else if (k < 3 * nz + 2) { const int i = node_of_bus[zb[a][k - 2 * nz - 2]]; kind = K_VM; ix = i; off = 2 * (A_VV * na + i); }
-      else if (k < 4 * nz + 2) { const int i = node_of_bus[zb[a][k - 3 * nz - 2]]; kind = K_VA; ix = i; off = 2 * (A_VV * na + i) + 1; }
+      else if (k < 3 * nz + 2) { const int i = node_of_bus[zb[a][k - 2 * nz - 2]]; kind = K_VM; ix = i; off = 2 * (i * kNodeArrays2 + A_VV); }
+      else if (k < 4 * nz + 2) { const int i = node_of_bus[zb[a][k - 3 * nz - 2]]; kind = K_VA; ix = i; off = 2 * (i * kNodeArrays2 + A_VV) + 1; }
       obs_src[idx] = (kind << 28) | ix;
       obs_off[idx] = static_cast<uint16_t>(off);
     }
   }
   obs_xptr[static_cast<size_t>(ng) * obs_dim] = static_cast<int>(obs_xidx.size());
+
+  // ---- 3a. line-loss table + scaling ----
+  std::vector<double> lscale = vec_or(net->load_scaling, nl, 1.0), sscale = vec_or(net->sgen_scaling, ng, 1.0);
+  std::vector<uint16_t> line_nodes;
+  std::vector<double> line_c;
+  for (int k = 0; k < nbr; ++k) {
+    if (!br_line[k]) continue;
+    const double* y = &e->ybr[8 * static_cast<size_t>(k)];
+    line_nodes.push_back(static_cast<uint16_t>(node_of_bus[e->br_from[k]]));
+    line_nodes.push_back(static_cast<uint16_t>(node_of_bus[e->br_to[k]]));
+    // pl = Re(Sf + St) = Gff|Vf|^2 + Gtt|Vt|^2 + (Gft+Gtf) Re(Vf Vt*) + (Bft-Btf) Im(Vf Vt*)   [x baseMVA]
+    line_c.push_back(y[0] * net->base_mva); line_c.push_back(y[6] * net->base_mva);
+    line_c.push_back((y[2] + y[4]) * net->base_mva); line_c.push_back((y[3] - y[5]) * net->base_mva);
+  }
+  const int n_line = static_cast<int>(line_nodes.size() / 2);
 
   // ---- 3b. hot static blob ----
   HotLayout hl{};
@@ -471,12 +528,12 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     int off = 0;
     auto take = [&](size_t bytes) { int o = off; off += static_cast<int>((bytes + 15) / 16 * 16); return o; };
     hl.yup = take(16 * npq); hl.ydn = take(16 * npq); hl.yii = take(16 * npq); hl.ysl = take(16 * npq);
-    hl.ndesc = take(8 * npq); hl.edesc = take(8 * npq); hl.enode = take(2 * npq);
-    hl.elev = take(2 * (n_lev + 1)); hl.dlev = take(2 * (n_lev + 1));
+    hl.ndesc = take(8 * npq); hl.esched = take(8 * esched.size()); hl.bsched = take(4 * bsched.size());
     hl.lptr = take(2 * lptr.size()); hl.lidx = take(2 * lidx.size());
     hl.sptr = take(2 * sptr.size()); hl.sidx = take(2 * sidx.size());
     hl.xptr = take(2 * xptr.size()); hl.xidx = take(2 * std::max<size_t>(1, xidx.size()));
     hl.node_of_bus = take(2 * n); hl.obs_off = take(2 * obs_off.size());
+    hl.line_nodes = take(2 * std::max<size_t>(1, line_nodes.size())); hl.line_c = take(8 * std::max<size_t>(1, line_c.size()));
     hl.bytes = off;
   }
   std::vector<unsigned char> hot(hl.bytes, 0);
@@ -486,8 +543,6 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     double* yup = reinterpret_cast<double*>(hot.data() + hl.yup); double* ydn = reinterpret_cast<double*>(hot.data() + hl.ydn);
     double* yii = reinterpret_cast<double*>(hot.data() + hl.yii); double* ysl = reinterpret_cast<double*>(hot.data() + hl.ysl);
     uint64_t* ndesc = reinterpret_cast<uint64_t*>(hot.data() + hl.ndesc);
-    uint64_t* edesc = reinterpret_cast<uint64_t*>(hot.data() + hl.edesc);
-    uint16_t* enode = reinterpret_cast<uint16_t*>(hot.data() + hl.enode);
     for (int i = 0; i < npq; ++i) {
       const int b = order[i];
       yii[2 * i] = e->ydiag[2 * b]; yii[2 * i + 1] = e->ydiag[2 * b + 1];
@@ -502,14 +557,13 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
         sl_node.push_back(i); sl_y.push_back(g); sl_y.push_back(bb);
       }
       // parent | child0 | child1 | number of further children (contiguous after child1); npq = zero slot
-      const uint64_t pa = parent[i] >= 0 ? static_cast<uint64_t>(parent[i]) : kNone;
+      const uint64_t pa = parent[i] >= 0 ? static_cast<uint64_t>(parent[i]) : npq;   // roots: sentinel, Y = 0
       const uint64_t c0 = nchild[i] > 0 ? cfirst[i] : npq, c1 = nchild[i] > 1 ? cfirst[i] + 1 : npq;
       const uint64_t nx = nchild[i] > 2 ? nchild[i] - 2 : 0;
       ndesc[i] = pa | (c0 << 16) | (c1 << 32) | (nx << 48);
     }
-    for (int k = 0; k < npq; ++k) { enode[k] = static_cast<uint16_t>(eorder[k]); edesc[k] = ndesc[eorder[k]]; }
-    std::memcpy(hot.data() + hl.elev, elev.data(), 2 * elev.size());
-    std::memcpy(hot.data() + hl.dlev, dlev.data(), 2 * dlev.size());
+    std::memcpy(hot.data() + hl.esched, esched.data(), 8 * esched.size());
+    std::memcpy(hot.data() + hl.bsched, bsched.data(), 4 * bsched.size());
     std::memcpy(hot.data() + hl.lptr, lptr.data(), 2 * lptr.size());
     if (nl) std::memcpy(hot.data() + hl.lidx, lidx.data(), 2 * static_cast<size_t>(nl));
     std::memcpy(hot.data() + hl.sptr, sptr.data(), 2 * sptr.size());
@@ -519,29 +573,16 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     uint16_t* nob = reinterpret_cast<uint16_t*>(hot.data() + hl.node_of_bus);
     for (int b = 0; b < n; ++b) nob[b] = static_cast<uint16_t>(node_of_bus[b]);
     std::memcpy(hot.data() + hl.obs_off, obs_off.data(), 2 * obs_off.size());
+    if (n_line) {
+      std::memcpy(hot.data() + hl.line_nodes, line_nodes.data(), 2 * line_nodes.size());
+      std::memcpy(hot.data() + hl.line_c, line_c.data(), 8 * line_c.size());
+    }
   }
-
-  // ---- 4. cold tables ----
-  std::vector<double> lscale = vec_or(net->load_scaling, nl, 1.0), sscale = vec_or(net->sgen_scaling, ng, 1.0);
-  std::vector<int> line_f, line_t;
-  std::vector<double> line_c;
-  for (int k = 0; k < nbr; ++k) {
-    if (!br_line[k]) continue;
-    const double* y = &e->ybr[8 * static_cast<size_t>(k)];
-    line_f.push_back(node_of_bus[e->br_from[k]]);
-    line_t.push_back(node_of_bus[e->br_to[k]]);
-    // pl = Re(Sf + St) = Gff|Vf|^2 + Gtt|Vt|^2 + (Gft+Gtf) Re(Vf Vt*) + (Bft-Btf) Im(Vf Vt*)   [x baseMVA]
-    line_c.push_back(y[0] * net->base_mva); line_c.push_back(y[6] * net->base_mva);
-    line_c.push_back((y[2] + y[4]) * net->base_mva); line_c.push_back((y[3] - y[5]) * net->base_mva);
-  }
-  const int n_line = static_cast<int>(line_f.size());
 
   // ---- 5. launch geometry ----
   cudaDeviceProp dp{};
   TRY_CUDA(cudaGetDeviceProperties(&dp, device));
-  int G = cfg->lanes_per_env;
-  if (G == 0) G = (npq <= 96) ? 8 : (npq <= 200 ? 16 : 32);
-  const int stride2 = env_stride2_for(npq, ng, G);
+  const int stride2 = env_stride2_for(npq, ng, nl, G);
   const size_t max_smem = dp.sharedMemPerBlockOptin;
   auto smem_for = [&](int w) { return static_cast<size_t>(hl.bytes) + static_cast<size_t>(w) * (32 / G) * stride2 * 16; };
   int warps = 4;
@@ -566,13 +607,13 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   Params& P = e->base;
   P.n_bus = n; P.npq = npq; P.n_load = nl; P.n_sgen = ng; P.n_line = n_line; P.n_lev = n_lev;
   P.obs_dim = obs_dim; P.state_dim = 4 * n + 2 * ng; P.n_slack_adj = static_cast<int>(sl_node.size());
+  P.n_esteps = n_esteps; P.n_bsteps = n_bsteps; P.has_extra_children = max_children > 2;
   P.slack_bus = slack;
-  P.nb = cfg->batch; P.env_stride2 = stride2; P.pvq_off2 = pvq_off2; P.hot_layout = hl;
+  P.nb = cfg->batch; P.env_stride2 = stride2; P.pvq_off2 = pvq_off2; P.scratch_off2 = scratch_off2; P.hot_layout = hl;
   std::vector<int> bus_of_node(order.begin(), order.end());
   TRY(dev_upload(e, hot, &P.hot));
   TRY(dev_upload(e, bus_of_node, &P.bus_of_node)); TRY(dev_upload(e, node_of_bus, &P.node_of_bus));
   TRY(dev_upload(e, lscale, &P.lscale)); TRY(dev_upload(e, sscale, &P.sscale));
-  TRY(dev_upload(e, line_f, &P.line_f)); TRY(dev_upload(e, line_t, &P.line_t)); TRY(dev_upload(e, line_c, &P.line_c));
   TRY(dev_upload(e, sl_node, &P.sl_node)); TRY(dev_upload(e, sl_y, &P.sl_y));
   TRY(dev_upload(e, obs_src, &P.obs_src)); TRY(dev_upload(e, obs_xptr, &P.obs_xptr)); TRY(dev_upload(e, obs_xidx, &P.obs_xidx));
   const size_t B = static_cast<size_t>(cfg->batch);

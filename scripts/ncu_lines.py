@@ -24,12 +24,10 @@ for ln in dis.splitlines():
         continue
     if not on:
         continue
-    mm = re.search(r'//## File ".*?", line (\d+)(.*)', ln)
+    mm = re.search(r'//## File "(.*?)", line (\d+)(.*)', ln)
     if mm:
-        if "inlined at" not in ln or cur is None:
-            cur = int(mm.group(1))
-        else:
-            cur = int(mm.group(1))
+        fn = os.path.basename(mm.group(1))
+        cur = int(mm.group(2)) if fn == "env_kernel.cuh" else -(int(mm.group(2)) + (100000 if "philox" in fn else 200000))
         continue
     mm = re.match(r"\s+/\*([0-9a-f]+)\*/\s+(.*?);", ln)
     if mm:
@@ -66,6 +64,9 @@ for (off, line, txt), r in zip(lines, data):
 src = open(os.path.join(ROOT, "mapdn_b200", "csrc", "env_kernel.cuh")).read().splitlines()
 print(f"{name}: {tot_s} samples, {tot_i} warp-instructions")
 for line, (s, ins, st) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
-    txt = src[line - 1].strip()[:70] if line and line <= len(src) else "?"
+    if line is not None and line < 0:
+        txt = ("philox.cuh:" if -line < 200000 else "other:") + str((-line) % 100000)
+    else:
+        txt = src[line - 1].strip()[:70] if line and line <= len(src) else "?"
     tops = ",".join(f"{k}:{v}" for k, v in st.most_common(3))
-    print(f"{line:4d} {s:5d} {100*s/tot_s:5.1f}%  inst {ins:9d} {100*ins/tot_i:5.1f}%  [{tops}]  {txt}")
+    print(f"{(line or 0):7d} {s:5d} {100*s/tot_s:5.1f}%  inst {ins:9d} {100*ins/tot_i:5.1f}%  [{tops}]  {txt}")
