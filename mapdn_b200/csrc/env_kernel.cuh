@@ -23,9 +23,6 @@
 
 namespace mapdn {
 
-#ifndef MAPDN_EXP
-#define MAPDN_EXP 0
-#endif
 #ifdef MAPDN_PROFILE
 #define PROF_DECL long long _pt = clock64(); long long _acc[12] = {0,0,0,0,0,0,0,0,0,0,0,0};
 #define PROF(k) { long long _t = clock64(); _acc[k] += _t - _pt; _pt = _t; }
@@ -146,8 +143,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // Views of the staged static blob and of one env's shared-memory slab.
 struct Hot {
   const double2 *yup, *ydn, *yii, *ysl;
-  const uint64_t *ndesc, *esched;
-  const uint32_t *bsched;
+  const uint64_t *ndesc, *esched, *bsched;
   const uint16_t *lptr, *lidx, *sptr, *sidx, *xptr, *xidx, *node_of_bus, *obs_off, *line_nodes;
   const double* line_c;
 };
@@ -248,42 +244,50 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
     __syncwarp();
     PROF(4)
     // --- forward elimination, leaves first: a flat schedule of steps (a level of the elimination forest,
-    //     split when it is wider than the group); one entry per (step, lane); idle lanes work on the trash
-    //     record, so the whole sweep is free of divergent branches ---
+    //     split when it is wider than the group), one entry per (step, lane). Lanes follow chains of the
+    //     forest: when a bus was eliminated by the same lane in the previous step, its Schur update reaches
+    //     the parent in registers (no shared-memory round trip on the critical path); the node's own blocks
+    //     are prefetched one step ahead. Idle lanes work on the trash record: no divergent branches. ---
     {
+      struct Own { double2 d01, d23, r, u, d; };
+      auto load_own = [&](uint64_t e) {
+        const double2* nd = s.node(static_cast<int>(e & 0xFFFFu));
+        Own o; o.d01 = nd[A_D01]; o.d23 = nd[A_D23]; o.r = nd[A_R]; o.u = nd[A_UP]; o.d = nd[A_DN];
+        return o;
+      };
       uint64_t ed = h.esched[gl];
+      uint64_t ed_next = h.esched[min(1, p.n_esteps - 1) * G + gl];
+      Own own = load_own(ed);
+      double2 s01 = make_double2(0.0, 0.0), s23 = s01, tt = s01;     // Schur update produced by this lane's last step
       for (int st = 0; st < p.n_esteps; ++st) {
-        const uint64_t ed_next = h.esched[min(st + 1, p.n_esteps - 1) * G + gl];   // independent of the data
+        const uint64_t ed_next2 = h.esched[min(st + 2, p.n_esteps - 1) * G + gl];   // independent of the data
+        const Own own_next = load_own(ed_next);          // not touched before its own step
         const int i = static_cast<int>(ed & 0xFFFFu);
         const int c0 = static_cast<int>((ed >> 16) & 0xFFFFu), c1 = static_cast<int>((ed >> 32) & 0xFFFFu);
+        const unsigned fl = static_cast<unsigned>(ed >> 48);
         double2* nd = s.node(i);
-        const double2* k0 = s.node(c0); const double2* k1 = s.node(c1);
-        // own blocks and edge terms (J[i,p] = [[a,b],[-b,a]](u), J[p,i] likewise (d); zero at roots): not
-        // touched by the previous steps, so they are loaded ahead of the barrier
-        double2 d01 = nd[A_D01], d23 = nd[A_D23], r = nd[A_R];
-        const double2 u = nd[A_UP], d = nd[A_DN];
-        __syncwarp();                                   // the previous step's Schur updates are visible
-#if MAPDN_EXP == 4
-        const double2 p01 = make_double2(0, 0), p23 = p01, pt = p01, q01 = p01, q23 = p01, qt = p01;
-#elif MAPDN_EXP == 7
-        const double2 p01 = k0[A_UP], p23 = k0[A_DN], pt = k0[A_T], q01 = make_double2(0, 0), q23 = q01, qt = q01;
-#else
-        const double2 p01 = k0[A_UP], p23 = k0[A_DN], pt = k0[A_T], q01 = k1[A_UP], q23 = k1[A_DN], qt = k1[A_T];
-#endif
+        double2 d01 = own.d01, d23 = own.d23, r = own.r;
+        const double2 u = own.u, d = own.d;   // J[i,p] = [[a,b],[-b,a]](u), J[p,i] likewise (d); zero at roots
+        __syncwarp();                                    // the previous step's Schur updates are visible
+        double2 p01 = s01, p23 = s23, pt = tt;           // child 0: registers ...
+        if (!(fl & kEschedReg0)) { p01 = make_double2(0.0, 0.0); p23 = p01; pt = p01; }
+        if (fl & kEschedLoad0) { const double2* k0 = s.node(c0); p01 = k0[A_UP]; p23 = k0[A_DN]; pt = k0[A_T]; }   // ... or smem
+        double2 q01 = make_double2(0.0, 0.0), q23 = q01, qt = q01;
+        if (fl & kEschedLoad1) { const double2* k1 = s.node(c1); q01 = k1[A_UP]; q23 = k1[A_DN]; qt = k1[A_T]; }
         d01.x -= p01.x + q01.x; d01.y -= p01.y + q01.y;
         d23.x -= p23.x + q23.x; d23.y -= p23.y + q23.y;
         r.x -= pt.x + qt.x; r.y -= pt.y + qt.y;
-        if (p.has_extra_children) {                     // warp-uniform
-          const int nx = static_cast<int>(ed >> 48);
+        if (p.has_extra_children) {                      // warp-uniform: only nets with a bus of degree > 3
+          const int nx = static_cast<int>(fl & 0xFFu);
 #pragma unroll 1
           for (int c = c1 + 1; c <= c1 + nx; ++c) {
             const double2* k = s.node(c);
-            const double2 s01 = k[A_UP], s23 = k[A_DN], t = k[A_T];
-            d01.x -= s01.x; d01.y -= s01.y; d23.x -= s23.x; d23.y -= s23.y;
-            r.x -= t.x; r.y -= t.y;
+            const double2 x01 = k[A_UP], x23 = k[A_DN], xt = k[A_T];
+            d01.x -= x01.x; d01.y -= x01.y; d23.x -= x23.x; d23.y -= x23.y;
+            r.x -= xt.x; r.y -= xt.y;
           }
         }
-        // adjugate form: everything that does not need 1/det runs beside the reciprocal
+        // adjugate form: everything that does not need 1/det runs beside the reciprocal (shorter chain, +8 flops)
         const double idet = fast_rcp(d01.x * d23.y - d01.y * d23.x);
         const double ca0 = d23.y * r.x - d01.y * r.y, ca1 = d01.x * r.y - d23.x * r.x;   // adj(D) r
         const double ma00 = d23.y * u.x + d01.y * u.y, ma01 = d23.y * u.y - d01.y * u.x; // adj(D) J[i,p]
@@ -291,38 +295,45 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
         const double sa00 = d.x * ma00 + d.y * ma10, sa01 = d.x * ma01 + d.y * ma11;     // J[p,i] adj(D) J[i,p]
         const double sa10 = d.x * ma10 - d.y * ma00, sa11 = d.x * ma11 - d.y * ma01;
         const double ta0 = d.x * ca0 + d.y * ca1, ta1 = d.x * ca1 - d.y * ca0;           // J[p,i] adj(D) r
-#if MAPDN_EXP == 5
-        if (sa00 * idet + sa10 * idet + ta0 * idet + ca0 * idet + ma00 * idet + ma10 * idet + sa01 + sa11 + ta1 + ca1 + ma01 + ma11 == 1.2345) nd[A_UP] = make_double2(1.0, 1.0);
-#elif MAPDN_EXP == 6
-        nd[A_UP] = make_double2(d01.x, d01.y); nd[A_DN] = make_double2(d23.x, d23.y); nd[A_T] = make_double2(r.x, r.y);
-        nd[A_R] = make_double2(u.x, u.y); nd[A_D01] = make_double2(d.x, d.y); nd[A_D23] = make_double2(idet, idet);
-#else
-        nd[A_UP] = make_double2(sa00 * idet, sa01 * idet);        // Schur update for the parent (zero at roots)
-        nd[A_DN] = make_double2(sa10 * idet, sa11 * idet);
-        nd[A_T] = make_double2(ta0 * idet, ta1 * idet);
-        nd[A_R] = make_double2(ca0 * idet, ca1 * idet);           // D^-1 r  (becomes dx in the back sweep)
-        nd[A_D01] = make_double2(ma00 * idet, ma01 * idet);       // D^-1 J[i,p]
-        nd[A_D23] = make_double2(ma10 * idet, ma11 * idet);
-#endif
-        ed = ed_next;
+        const double c0v = ca0 * idet, c1v = ca1 * idet;
+        const double m00 = ma00 * idet, m01 = ma01 * idet, m10 = ma10 * idet, m11 = ma11 * idet;
+        s01 = make_double2(sa00 * idet, sa01 * idet);
+        s23 = make_double2(sa10 * idet, sa11 * idet);
+        tt = make_double2(ta0 * idet, ta1 * idet);
+        nd[A_UP] = s01; nd[A_DN] = s23; nd[A_T] = tt;
+        nd[A_R] = make_double2(c0v, c1v);                         // D^-1 r  (becomes dx in the back sweep)
+        nd[A_D01] = make_double2(m00, m01);                       // D^-1 J[i,p]
+        nd[A_D23] = make_double2(m10, m11);
+        ed = ed_next; ed_next = ed_next2; own = own_next;
       }
     }
     PROF(5)
-    // --- back substitution root -> leaves, same flat-schedule form (roots: dx = D^-1 r already) ---
+    // --- back substitution root -> leaves, same flat-schedule form (roots: dx = D^-1 r already); a lane
+    //     that solved the parent in the previous step keeps dx_parent in registers ---
     {
-      uint32_t bd = h.bsched[gl];
+      struct OwnB { double2 m01, m23, x; };
+      auto load_own = [&](uint64_t e) {
+        const double2* nd = s.node(static_cast<int>(e & 0xFFFFu));
+        OwnB o; o.m01 = nd[A_D01]; o.m23 = nd[A_D23]; o.x = nd[A_R];
+        return o;
+      };
+      uint64_t bd = h.bsched[gl];
+      uint64_t bd_next = h.bsched[min(1, p.n_bsteps - 1) * G + gl];
+      OwnB own = load_own(bd);
+      double2 xl = make_double2(0.0, 0.0);               // dx of the node this lane solved in the previous step
       for (int st = 0; st < p.n_bsteps; ++st) {
-        const uint32_t bd_next = h.bsched[min(st + 1, p.n_bsteps - 1) * G + gl];
+        const uint64_t bd_next2 = h.bsched[min(st + 2, p.n_bsteps - 1) * G + gl];
+        const OwnB own_next = load_own(bd_next);         // D^-1 J and D^-1 r are final since the forward sweep
         double2* nd = s.node(static_cast<int>(bd & 0xFFFFu));
-        const double2* np = s.node(static_cast<int>(bd >> 16));
-        const double2 m01 = nd[A_D01], m23 = nd[A_D23];
-        double2 x = nd[A_R];
-        __syncwarp();                                   // the previous step's dx are visible
-        const double2 xp = np[A_R];
-        x.x -= m01.x * xp.x + m01.y * xp.y;
-        x.y -= m23.x * xp.x + m23.y * xp.y;
+        __syncwarp();                                    // the previous step's dx are visible
+        double2 xp = xl;
+        if (!((bd >> 32) & 1u)) xp = s.node(static_cast<int>((bd >> 16) & 0xFFFFu))[A_R];
+        double2 x = own.x;
+        x.x -= own.m01.x * xp.x + own.m01.y * xp.y;
+        x.y -= own.m23.x * xp.x + own.m23.y * xp.y;
         nd[A_R] = x;
-        bd = bd_next;
+        xl = x;
+        bd = bd_next; bd_next = bd_next2; own = own_next;
       }
       __syncwarp();
     }
@@ -368,7 +379,7 @@ __global__ void __launch_bounds__(128) env_kernel(const __grid_constant__ Params
   h.ysl = reinterpret_cast<const double2*>(smem_raw + hl.ysl);
   h.ndesc = reinterpret_cast<const uint64_t*>(smem_raw + hl.ndesc);
   h.esched = reinterpret_cast<const uint64_t*>(smem_raw + hl.esched);
-  h.bsched = reinterpret_cast<const uint32_t*>(smem_raw + hl.bsched);
+  h.bsched = reinterpret_cast<const uint64_t*>(smem_raw + hl.bsched);
   h.lptr = reinterpret_cast<const uint16_t*>(smem_raw + hl.lptr);
   h.lidx = reinterpret_cast<const uint16_t*>(smem_raw + hl.lidx);
   h.sptr = reinterpret_cast<const uint16_t*>(smem_raw + hl.sptr);

@@ -26,14 +26,18 @@ enum NodeArr2 {           // index of the double2 field inside a node record
 constexpr int A_BP = A_D01;   // res_bus (p_mw, q_mvar) per node
 constexpr int A_OP = A_D23;   // "demand" columns of get_obs: res_bus p/q + sgen add-back (reference :238-244)
 constexpr uint32_t kNone = 0xFFFFu;   // "no parent" in 16-bit node fields
+// esched flags: low 8 bits = number of children beyond two; then where child 0's Schur update comes from
+constexpr unsigned kEschedReg0 = 0x100u;    // registers of the same lane (it eliminated child 0 in the previous step)
+constexpr unsigned kEschedLoad0 = 0x200u;   // shared memory
+constexpr unsigned kEschedLoad1 = 0x400u;   // child 1 exists (always from shared memory)
 
 struct HotLayout {        // byte offsets inside the hot static blob (staged into smem per CTA)
   int yup, ydn;           // double2 [npq]: Y[i,parent], Y[parent,i]   (G, B)
   int yii, ysl;           // double2 [npq]: Y[i,i], Y[i,slack]
   int ndesc;              // uint64 [npq]: parent | c0<<16 | c1<<32 | cextra_first<<48 ... see make_ndesc
   int esched;             // uint64 [n_esteps * G]: elimination schedule, one entry per (step, lane):
-                          //   node | child0<<16 | child1<<32 | n_extra_children<<48   (idle lane: trash record)
-  int bsched;             // uint32 [n_bsteps * G]: back-substitution schedule: node | parent<<16
+                          //   node | child0<<16 | child1<<32 | flags<<48   (idle lane: trash record)
+  int bsched;             // uint64 [n_bsteps * G]: back-substitution schedule: node | parent<<16 | reg_parent<<32
   int lptr, lidx;         // uint16 [npq+2], [n_load]: node -> loads (CSR); node npq = slack bus
   int sptr, sidx;         // uint16 [npq+2], [n_sgen]: node -> sgens
   int xptr, xidx;         // uint16 [npq+2], [<=n_sgen]: node -> sgens of the node's own zone (obs add-back)

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -427,26 +428,86 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   for (int i = 0; i < npq; ++i) max_children = std::max(max_children, nchild[i]);
   int G = cfg->lanes_per_env;
   if (G == 0) G = (npq <= 96) ? 8 : (npq <= 200 ? 16 : 32);
-  // flat schedules for this G: a level wider than G takes several steps; idle lanes get the trash record
+  // Flat schedules for this G: a level wider than G takes several steps; idle lanes get the trash record.
+  // Lanes follow chains: a bus is placed on the lane that handled its child (forward sweep) / its parent
+  // (back sweep) in the immediately preceding step whenever that lane is free, so the dependent value can
+  // stay in registers.
   const int trash = npq + 1;
-  std::vector<uint64_t> esched;
-  std::vector<uint32_t> bsched;
-  auto edesc_of = [&](int i) {
-    const uint64_t c0 = nchild[i] > 0 ? cfirst[i] : npq, c1 = nchild[i] > 1 ? cfirst[i] + 1 : npq;
-    const uint64_t nx = nchild[i] > 2 ? nchild[i] - 2 : 0;
-    return static_cast<uint64_t>(i) | (c0 << 16) | (c1 << 32) | (nx << 48);
-  };
-  const uint64_t e_idle = static_cast<uint64_t>(trash) | (static_cast<uint64_t>(npq) << 16) | (static_cast<uint64_t>(npq) << 32);
-  for (int l = 0; l < n_lev; ++l)
-    for (int b0 = elev[l]; b0 < elev[l + 1]; b0 += G)
-      for (int g = 0; g < G; ++g) esched.push_back(b0 + g < elev[l + 1] ? edesc_of(eorder[b0 + g]) : e_idle);
-  const uint32_t b_idle = static_cast<uint32_t>(trash) | (static_cast<uint32_t>(npq) << 16);
-  for (int l = 1; l < n_lev; ++l)
-    for (int b0 = dlev[l]; b0 < dlev[l + 1]; b0 += G)
-      for (int g = 0; g < G; ++g)
-        bsched.push_back(b0 + g < dlev[l + 1] ? (static_cast<uint32_t>(b0 + g) | (static_cast<uint32_t>(parent[b0 + g]) << 16)) : b_idle);
+  std::vector<uint64_t> esched, bsched;
+  {
+    std::vector<int> lane_of(npq, -1), step_of(npq, -1);
+    int cur = 0;
+    for (int l = 0; l < n_lev; ++l) {
+      const int w = elev[l + 1] - elev[l], nst = (w + G - 1) / G;
+      std::vector<int> slot(static_cast<size_t>(nst) * G, -1), inh(npq, -1);
+      std::vector<int> rest;
+      for (int k = elev[l]; k < elev[l + 1]; ++k) {
+        const int i = eorder[k];
+        int pick = -1;
+        if (nchild[i] >= 1 && nchild[i] <= 2)
+          for (int c = cfirst[i]; c < cfirst[i] + nchild[i]; ++c)
+            if (step_of[c] == cur - 1 && slot[lane_of[c]] < 0 && (pick < 0 || height[c] > height[pick])) pick = c;
+        if (pick >= 0) { slot[lane_of[pick]] = i; inh[i] = pick; }
+        else rest.push_back(i);
+      }
+      size_t pos = 0;
+      for (int i : rest) { while (slot[pos] >= 0) ++pos; slot[pos] = i; }
+      for (int sidx = 0; sidx < nst * G; ++sidx) {
+        const int i = slot[sidx];
+        if (i < 0) { esched.push_back(static_cast<uint64_t>(trash) | (static_cast<uint64_t>(npq) << 16) |
+                                      (static_cast<uint64_t>(npq) << 32) | (static_cast<uint64_t>(kEschedReg0) << 48)); continue; }
+        lane_of[i] = sidx % G; step_of[i] = cur + sidx / G;
+        uint64_t c0 = npq, c1 = npq, fl = 0;
+        if (nchild[i] > 2) {
+          c0 = cfirst[i]; c1 = cfirst[i] + 1; fl = static_cast<uint64_t>(std::min(nchild[i] - 2, 255)) | kEschedLoad0 | kEschedLoad1;
+          if (nchild[i] - 2 > 255) return bail(fail(MAPDN_ERR_UNSUPPORTED, "a bus with more than 257 children"));
+        } else if (nchild[i] >= 1) {
+          const int a0 = inh[i] >= 0 ? inh[i] : cfirst[i];
+          c0 = a0; fl = (inh[i] >= 0 && sidx / G == 0) ? kEschedReg0 : kEschedLoad0;
+          if (nchild[i] == 2) { c1 = (a0 == cfirst[i]) ? cfirst[i] + 1 : cfirst[i]; fl |= kEschedLoad1; }
+        }
+        esched.push_back(static_cast<uint64_t>(i) | (c0 << 16) | (c1 << 32) | (fl << 48));
+      }
+      cur += nst;
+    }
+    // back sweep by depth: children inherit the lane of their parent (the child with the tallest subtree first)
+    std::fill(lane_of.begin(), lane_of.end(), -1); std::fill(step_of.begin(), step_of.end(), -1);
+    cur = 0;
+    for (int l = 1; l < n_lev; ++l) {
+      const int w = dlev[l + 1] - dlev[l], nst = (w + G - 1) / G;
+      std::vector<int> slot(static_cast<size_t>(nst) * G, -1);
+      std::vector<char> reg(npq, 0);
+      std::vector<int> nodes;
+      for (int i = dlev[l]; i < dlev[l + 1]; ++i) nodes.push_back(i);
+      std::stable_sort(nodes.begin(), nodes.end(), [&](int a, int b) { return height[a] > height[b]; });
+      std::vector<int> rest;
+      for (int i : nodes) {
+        const int pa = parent[i];
+        if (step_of[pa] == cur - 1 && lane_of[pa] >= 0 && slot[lane_of[pa]] < 0) { slot[lane_of[pa]] = i; reg[i] = 1; }
+        else rest.push_back(i);
+      }
+      size_t pos = 0;
+      for (int i : rest) { while (slot[pos] >= 0) ++pos; slot[pos] = i; }
+      for (int sidx = 0; sidx < nst * G; ++sidx) {
+        const int i = slot[sidx];
+        if (i < 0) { bsched.push_back(static_cast<uint64_t>(trash) | (static_cast<uint64_t>(npq) << 16) | (1ull << 32)); continue; }
+        lane_of[i] = sidx % G; step_of[i] = cur + sidx / G;
+        bsched.push_back(static_cast<uint64_t>(i) | (static_cast<uint64_t>(parent[i]) << 16) |
+                         (static_cast<uint64_t>(reg[i] && sidx / G == 0) << 32));
+      }
+      cur += nst;
+    }
+  }
+  if (getenv("MAPDN_DEBUG_SCHED")) {
+    int nreg = 0, nl0 = 0, nl1 = 0, nreal = 0;
+    for (uint64_t e2 : esched) { if ((e2 & 0xFFFF) == (uint64_t)trash) continue; ++nreal; unsigned fl = e2 >> 48; nreg += !!(fl & kEschedReg0); nl0 += !!(fl & kEschedLoad0); nl1 += !!(fl & kEschedLoad1); }
+    int breg = 0, breal = 0;
+    for (uint64_t b2 : bsched) { if ((b2 & 0xFFFF) == (uint64_t)trash) continue; ++breal; breg += (b2 >> 32) & 1; }
+    fprintf(stderr, "[sched] G=%d levels=%d esteps=%zu real=%d reg0=%d load0=%d load1=%d | bsteps=%zu real=%d regp=%d\n", G, n_lev,
+            esched.size() / G, nreal, nreg, nl0, nl1, bsched.size() / G, breal, breg);
+  }
   const int n_esteps = static_cast<int>(esched.size()) / G, n_bsteps = static_cast<int>(bsched.size()) / G;
-  if (bsched.empty()) bsched.assign(G, b_idle);
+  if (bsched.empty()) bsched.assign(G, static_cast<uint64_t>(trash) | (static_cast<uint64_t>(npq) << 16) | (1ull << 32));
 
   // ---- 3. element -> node maps (needed by the hot blob) ----
   const int na = npq + 2;      // + sentinel + trash records
@@ -528,7 +589,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     int off = 0;
     auto take = [&](size_t bytes) { int o = off; off += static_cast<int>((bytes + 15) / 16 * 16); return o; };
     hl.yup = take(16 * npq); hl.ydn = take(16 * npq); hl.yii = take(16 * npq); hl.ysl = take(16 * npq);
-    hl.ndesc = take(8 * npq); hl.esched = take(8 * esched.size()); hl.bsched = take(4 * bsched.size());
+    hl.ndesc = take(8 * npq); hl.esched = take(8 * esched.size()); hl.bsched = take(8 * bsched.size());
     hl.lptr = take(2 * lptr.size()); hl.lidx = take(2 * lidx.size());
     hl.sptr = take(2 * sptr.size()); hl.sidx = take(2 * sidx.size());
     hl.xptr = take(2 * xptr.size()); hl.xidx = take(2 * std::max<size_t>(1, xidx.size()));
@@ -563,7 +624,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
       ndesc[i] = pa | (c0 << 16) | (c1 << 32) | (nx << 48);
     }
     std::memcpy(hot.data() + hl.esched, esched.data(), 8 * esched.size());
-    std::memcpy(hot.data() + hl.bsched, bsched.data(), 4 * bsched.size());
+    std::memcpy(hot.data() + hl.bsched, bsched.data(), 8 * bsched.size());
     std::memcpy(hot.data() + hl.lptr, lptr.data(), 2 * lptr.size());
     if (nl) std::memcpy(hot.data() + hl.lidx, lidx.data(), 2 * static_cast<size_t>(nl));
     std::memcpy(hot.data() + hl.sptr, sptr.data(), 2 * sptr.size());
