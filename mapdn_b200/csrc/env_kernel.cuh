@@ -66,6 +66,35 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return fma(r, e, r);
 }
 
+// sin/cos for the bus angles: distribution-feeder angles are a few degrees, so the common path is a pair of
+// Taylor polynomials on |x| <= pi/4 (truncation < 1e-19, i.e. exact to rounding; two independent FMA chains,
+// no range reduction); larger angles fall back to the library routine.
+__device__ __forceinline__ void sincos_angle(double x, double* sn, double* cs) {
+  if (fabs(x) <= 0.78539816339744830962) {
+    const double z = x * x;
+    double ps = 1.0 / 355687428096000.0;                 // 1/17!
+    ps = fma(ps, z, -1.0 / 1307674368000.0);             // -1/15!
+    ps = fma(ps, z, 1.0 / 6227020800.0);                 // 1/13!
+    ps = fma(ps, z, -1.0 / 39916800.0);                  // -1/11!
+    ps = fma(ps, z, 1.0 / 362880.0);                     // 1/9!
+    ps = fma(ps, z, -1.0 / 5040.0);                      // -1/7!
+    ps = fma(ps, z, 1.0 / 120.0);                        // 1/5!
+    ps = fma(ps, z, -1.0 / 6.0);                         // -1/3!
+    double pc = 1.0 / 20922789888000.0;                  // 1/16!
+    pc = fma(pc, z, -1.0 / 87178291200.0);               // -1/14!
+    pc = fma(pc, z, 1.0 / 479001600.0);                  // 1/12!
+    pc = fma(pc, z, -1.0 / 3628800.0);                   // -1/10!
+    pc = fma(pc, z, 1.0 / 40320.0);                      // 1/8!
+    pc = fma(pc, z, -1.0 / 720.0);                       // -1/6!
+    pc = fma(pc, z, 1.0 / 24.0);                         // 1/4!
+    pc = fma(pc, z, -0.5);                               // -1/2!
+    *sn = fma(ps * z, x, x);
+    *cs = fma(pc, z, 1.0);
+  } else {
+    sincos(x, sn, cs);
+  }
+}
+
 // exp(x) for x in [-0.125, 0] (the only range the bowl barrier needs): degree-9 Taylor, |err| < 3e-15
 __device__ __forceinline__ double exp_small(double x) {
   double r = 1.0 / 362880.0;
@@ -348,7 +377,7 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
         v.y += x.x;
         v.x += v.x * x.y;
         double sn, cs;
-        sincos(v.y, &sn, &cs);
+        sincos_angle(v.y, &sn, &cs);
         nd[A_VV] = v;
         nd[A_EF] = make_double2(v.x * cs, v.x * sn);
       }

@@ -427,7 +427,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   for (int l = 0; l < n_lev; ++l) max_width = std::max(max_width, elev[l + 1] - elev[l]);
   for (int i = 0; i < npq; ++i) max_children = std::max(max_children, nchild[i]);
   int G = cfg->lanes_per_env;
-  if (G == 0) G = (npq <= 96) ? 8 : (npq <= 200 ? 16 : 32);
+  if (G == 0) G = (npq <= 64) ? 8 : 32;     // measured on B200: 8 lanes/env for 33-bus feeders, a full warp beyond
   // Flat schedules for this G: a level wider than G takes several steps; idle lanes get the trash record.
   // Lanes follow chains: a bus is placed on the lane that handled its child (forward sweep) / its parent
   // (back sweep) in the immediately preceding step whenever that lane is free, so the dependent value can
