@@ -34,7 +34,7 @@ constexpr unsigned kEschedLoad1 = 0x400u;   // child 1 exists (always from share
 struct HotLayout {        // byte offsets inside the hot static blob (staged into smem per CTA)
   int yup, ydn;           // double2 [npq]: Y[i,parent], Y[parent,i]   (G, B)
   int yii, ysl;           // double2 [npq]: Y[i,i], Y[i,slack]
-  int ndesc;              // uint64 [npq]: parent | c0<<16 | c1<<32 | cextra_first<<48 ... see make_ndesc
+  int ndesc;              // uint64 [npq]: node descriptor, see below
   int esched;             // uint64 [n_esteps * G]: elimination schedule, one entry per (step, lane):
                           //   node | child0<<16 | child1<<32 | flags<<48   (idle lane: trash record)
   int bsched;             // uint64 [n_bsteps * G]: back-substitution schedule: node | parent<<16 | reg_parent<<32
@@ -48,8 +48,8 @@ struct HotLayout {        // byte offsets inside the hot static blob (staged int
   int bytes;              // total, multiple of 16
 };
 
-// node descriptor (64 bit): parent(16) | child0(16) | child1(16) | n_extra(8) | extra_first... packed as:
-//   bits  0-15 parent (kNone for roots)
+// node descriptor (64 bit):
+//   bits  0-15 parent (the sentinel record npq for roots: zero admittance)
 //   bits 16-31 first child  (npq = none -> zero slot)
 //   bits 32-47 second child (npq = none)
 //   bits 48-63 number of children beyond two (they follow child1 contiguously)
@@ -65,7 +65,6 @@ struct Params {
   const unsigned char* hot;
   // ---- cold static (global, read through the read-only path) ----
   const int* bus_of_node;                                     // [npq]
-  const int* node_of_bus;                                     // [n_bus]; slack -> npq
   const double* lscale; const double* sscale;                 // scaling by load id / sgen id
   const int* sl_node; const double* sl_y;                     // slack-adjacent nodes, Y[slack,i] (G,B)
   const unsigned* obs_src; const int* obs_xptr; const int* obs_xidx;   // cold obs program of get_obs_kernel

@@ -146,9 +146,9 @@ struct mapdn_env {
   // Ybus pieces kept for the test hook
   std::vector<double> ybr, ydiag;
   std::vector<int> br_from, br_to;
-  // staging buffers of the *_host entry points
-  double *h_actions = nullptr, *h_reward = nullptr, *h_info = nullptr, *h_obs = nullptr;
-  unsigned char* h_term = nullptr;
+  // device-side staging buffers of the *_host entry points
+  double *d_stage_actions = nullptr, *d_stage_reward = nullptr, *d_stage_info = nullptr, *d_stage_obs = nullptr;
+  unsigned char* d_stage_term = nullptr;
 };
 
 namespace {
@@ -673,7 +673,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   P.nb = cfg->batch; P.env_stride2 = stride2; P.pvq_off2 = pvq_off2; P.scratch_off2 = scratch_off2; P.hot_layout = hl;
   std::vector<int> bus_of_node(order.begin(), order.end());
   TRY(dev_upload(e, hot, &P.hot));
-  TRY(dev_upload(e, bus_of_node, &P.bus_of_node)); TRY(dev_upload(e, node_of_bus, &P.node_of_bus));
+  TRY(dev_upload(e, bus_of_node, &P.bus_of_node));
   TRY(dev_upload(e, lscale, &P.lscale)); TRY(dev_upload(e, sscale, &P.sscale));
   TRY(dev_upload(e, sl_node, &P.sl_node)); TRY(dev_upload(e, sl_y, &P.sl_y));
   TRY(dev_upload(e, obs_src, &P.obs_src)); TRY(dev_upload(e, obs_xptr, &P.obs_xptr)); TRY(dev_upload(e, obs_xidx, &P.obs_xidx));
@@ -721,8 +721,8 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   TRY(dev_alloc(e, B, &P.steps)); TRY(dev_alloc(e, B, &P.sum_rewards));
   TRY(dev_alloc(e, B, &P.start_row)); TRY(dev_alloc(e, B, &P.episode));
   // staging for the *_host entry points
-  TRY(dev_alloc(e, B * ng, &e->h_actions)); TRY(dev_alloc(e, B, &e->h_reward)); TRY(dev_alloc(e, B, &e->h_term));
-  TRY(dev_alloc(e, B * MAPDN_N_INFO, &e->h_info)); TRY(dev_alloc(e, B * ng * obs_dim, &e->h_obs));
+  TRY(dev_alloc(e, B * ng, &e->d_stage_actions)); TRY(dev_alloc(e, B, &e->d_stage_reward)); TRY(dev_alloc(e, B, &e->d_stage_term));
+  TRY(dev_alloc(e, B * MAPDN_N_INFO, &e->d_stage_info)); TRY(dev_alloc(e, B * ng * obs_dim, &e->d_stage_obs));
 
   mapdn_dims& d = e->dims;
   d.batch = cfg->batch; d.n_bus = n; d.n_branch = nbr; d.n_line = n_line; d.n_load = nl; d.n_sgen = ng;
@@ -772,14 +772,14 @@ mapdn_status mapdn_step_host(mapdn_env* e, const double* actions_host, int32_t a
   MAPDN_CUDA(cudaSetDevice(e->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t B = e->dims.batch, ng = e->dims.n_sgen, od = e->dims.obs_dim;
-  MAPDN_CUDA(cudaMemcpyAsync(e->h_actions, actions_host, B * ng * sizeof(double), cudaMemcpyHostToDevice, st));
-  mapdn_status s = mapdn_step(e, e->h_actions, add_noise, e->h_reward, e->h_term, info_host ? e->h_info : nullptr,
-                              obs_host ? e->h_obs : nullptr, stream);
+  MAPDN_CUDA(cudaMemcpyAsync(e->d_stage_actions, actions_host, B * ng * sizeof(double), cudaMemcpyHostToDevice, st));
+  mapdn_status s = mapdn_step(e, e->d_stage_actions, add_noise, e->d_stage_reward, e->d_stage_term, info_host ? e->d_stage_info : nullptr,
+                              obs_host ? e->d_stage_obs : nullptr, stream);
   if (s != MAPDN_OK) return s;
-  MAPDN_CUDA(cudaMemcpyAsync(reward_host, e->h_reward, B * sizeof(double), cudaMemcpyDeviceToHost, st));
-  MAPDN_CUDA(cudaMemcpyAsync(terminated_host, e->h_term, B, cudaMemcpyDeviceToHost, st));
-  if (info_host) MAPDN_CUDA(cudaMemcpyAsync(info_host, e->h_info, B * MAPDN_N_INFO * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (obs_host) MAPDN_CUDA(cudaMemcpyAsync(obs_host, e->h_obs, B * ng * od * sizeof(double), cudaMemcpyDeviceToHost, st));
+  MAPDN_CUDA(cudaMemcpyAsync(reward_host, e->d_stage_reward, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  MAPDN_CUDA(cudaMemcpyAsync(terminated_host, e->d_stage_term, B, cudaMemcpyDeviceToHost, st));
+  if (info_host) MAPDN_CUDA(cudaMemcpyAsync(info_host, e->d_stage_info, B * MAPDN_N_INFO * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (obs_host) MAPDN_CUDA(cudaMemcpyAsync(obs_host, e->d_stage_obs, B * ng * od * sizeof(double), cudaMemcpyDeviceToHost, st));
   MAPDN_CUDA(cudaStreamSynchronize(st));
   return MAPDN_OK;
 }

@@ -224,3 +224,45 @@ def test_voltage_control_shim_api():
     obs, state = env.reset()
     assert env.steps == 1 and env.sum_rewards == 0
     env.close()
+
+
+def test_step_is_cuda_graph_capturable():
+    """mapdn_step is stream-ordered (no sync, no allocation): a rollout inner loop can be captured in a CUDA graph."""
+    net, prof = cases.make_case("case33"), cases.make_profiles("case33", n_days=4)
+    e1 = _make(net, prof, dict(seed=8, voltage_barrier_type="bowl"), batch=128)
+    e2 = _make(net, prof, dict(seed=8, voltage_barrier_type="bowl"), batch=128)
+    e1.reset(); e2.reset()
+    a = torch.zeros(128, 6, dtype=torch.float64, device=e1.device).uniform_(-0.8, 0.8)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        e1.step(a)                                   # warm-up on the side stream
+    torch.cuda.current_stream().wait_stream(s)
+    e2.step(a)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(4):
+            e1.step(a)
+    g.replay()
+    for _ in range(4):
+        e2.step(a)
+    torch.cuda.synchronize()
+    assert torch.equal(e1.reward, e2.reward) and torch.equal(e1.obs, e2.obs)
+    assert torch.equal(e1.get_field("steps"), e2.get_field("steps"))
+
+
+def test_shim_history_and_reset_time():
+    """history > 1 stacking (reference :303-315) and reset(reset_time=False) keeping the episode start (:110-113)."""
+    from mapdn_b200.env import VoltageControl
+    env = VoltageControl(dict(scenario="case33", voltage_barrier_type="l1", history=3, seed=1, data_path="unused"))
+    assert env.get_obs_size() == 3 * 50
+    o1 = env.get_obs()
+    assert o1[0].shape == (150,)
+    env.step(np.zeros(6))
+    o2 = env.get_obs()
+    assert np.array_equal(o2[0][50:100], o1[0][100:150])          # the previous newest frame moved back one slot
+    start = (env._episode_start_day, env._episode_start_hour, env._episode_start_interval)
+    env.reset(reset_time=False)
+    assert (env._episode_start_day, env._episode_start_hour, env._episode_start_interval) == start
+    env.reset()
+    env.close()
