@@ -7,6 +7,8 @@
 // admittances, the elimination schedule, the element->bus maps and the observation program
 // (identical for all envs) are staged once per CTA with a TMA bulk copy. The Newton loop never
 // touches HBM and is written branch-light: every "missing child" points at an all-zero slot.
+// In MODE_STEP one extra (helper) warp per CTA draws the next profile rows + noise of the CTA's
+// envs concurrently with the Newton iteration (warp specialisation, two named barriers).
 //
 // The linear solve works on the forest of PQ buses (the slack bus is not an unknown), each tree
 // re-rooted at its centre so that the leaf->root elimination has half the depth of the feeder.
@@ -159,14 +161,13 @@ __device__ __forceinline__ void stage_hot_wait(uint64_t* bar) {
   }
 }
 
-// 8-byte asynchronous global -> shared copy (LDGSTS): prefetch of the next profile row
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
-               "l"(gsrc)
-               : "memory");
+// Named barriers between the solver warps and the helper warp of a CTA (producer / consumer)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // Views of the staged static blob and of one env's shared-memory slab.
@@ -393,7 +394,7 @@ __device__ __forceinline__ double clip_q(double a, double pv, double smax) {
 }
 
 template <int G, int MODE>
-__global__ void __launch_bounds__(128) env_kernel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(160) env_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t stage_bar;
   PROF_DECL
@@ -420,9 +421,14 @@ __global__ void __launch_bounds__(128) env_kernel(const __grid_constant__ Params
   h.line_nodes = reinterpret_cast<const uint16_t*>(smem_raw + hl.line_nodes);
   h.line_c = reinterpret_cast<const double*>(smem_raw + hl.line_c);
 
+  // MODE_STEP: the last warp of the CTA is a helper that draws the next profile rows (+ noise) of the CTA's
+  // envs while the solver warps run the Newton iteration (the two only meet at two named barriers)
+  const int n_solver_threads = blockDim.x - ((MODE == MODE_STEP) ? 32 : 0);
+  const bool is_helper = (MODE == MODE_STEP) && threadIdx.x >= n_solver_threads;
+  const int hl_bytes = p.hot_layout.bytes;
   const int gl = threadIdx.x % G;
-  const int gidx = threadIdx.x / G;
-  const int epb = blockDim.x / G;
+  const int gidx = is_helper ? 0 : threadIdx.x / G;
+  const int epb = n_solver_threads / G;
   const int npq = p.npq, n = p.n_bus, nl = p.n_load, ng = p.n_sgen;
   Slab s;
   {
@@ -435,10 +441,49 @@ __global__ void __launch_bounds__(128) env_kernel(const __grid_constant__ Params
   }
   double* stage_pl = s.scratch;          // prologue: scaled load p / q
   double* stage_ql = s.scratch + nl;
-  double* next_row = s.scratch;          // after the prologue: [pv | load_p | load_q] of the next profile row
+  double* next_row = s.scratch;          // after the prologue: the helper warp's new sgen.p_mw [n_sgen]
   const uint32_t k0 = static_cast<uint32_t>(p.seed), k1 = static_cast<uint32_t>(p.seed >> 32);
 
   for (int base = blockIdx.x * epb; base < p.nb; base += gridDim.x * epb) {
+    if (is_helper) {
+      // ---- helper warp: next profile row of every env of this round (reference _set_demand_and_pv :491-513:
+      //      t = self.steps before the increment) + |N(0,1)| * std noise in Box-Muller pairs (2m, 2m+1) over the
+      //      elements [pv | load_p | load_q]; new pv goes to the env's scratch (for the obs), loads straight to HBM ----
+      named_bar_sync(1, blockDim.x);                   // the solvers have read the current rows
+      const int n_elem = ng + 2 * nl, n_pair = (n_elem + 1) / 2;
+      const int hl = threadIdx.x - n_solver_threads;
+      for (int w = hl; w < epb * n_pair; w += 32) {
+        const int e = w / n_pair, m = w - e * n_pair, env_h = base + e;
+        if (env_h >= p.nb) continue;
+        const int steps_h = p.steps[env_h];
+        long long nrow = p.start_row[env_h] + steps_h;
+        if (nrow > p.n_rows - 1) nrow = p.n_rows - 1;
+        RngKey key_h{k0, k1, static_cast<uint32_t>(p.env_id_offset + env_h), p.episode[env_h] * 8u};
+        double z[2] = {0.0, 0.0};
+        if (p.add_noise) half_normal_pair(key_h, static_cast<uint32_t>(steps_h), m, z[0], z[1]);
+        double* pv_next = reinterpret_cast<double*>(reinterpret_cast<double2*>(smem_raw + hl_bytes) +
+                                                     static_cast<size_t>(e) * p.env_stride2 + p.scratch_off2);
+        const size_t hL = static_cast<size_t>(env_h) * nl, hG = static_cast<size_t>(env_h) * ng;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int el = 2 * m + u;
+          if (el >= n_elem) break;
+          if (el < ng) {
+            const double pv = __ldg(p.prof_pv + nrow * ng + el) + __ldg(p.pv_std + el) * z[u];
+            pv_next[el] = pv;
+            p.cur_pv[hG + el] = pv;
+          } else if (el < ng + nl) {
+            const int l = el - ng;
+            p.cur_pl[hL + l] = __ldg(p.prof_lp + nrow * nl + l) + __ldg(p.lp_std + l) * z[u];
+          } else {
+            const int l = el - ng - nl;
+            p.cur_ql[hL + l] = __ldg(p.prof_lq + nrow * nl + l) + __ldg(p.lq_std + l) * z[u];
+          }
+        }
+      }
+      named_bar_arrive(2, blockDim.x);                 // new pv of every env is in shared memory
+      continue;
+    }
     int env = base + gidx;
     bool valid = env < p.nb;
     if (!valid) env = p.nb - 1;
@@ -533,17 +578,7 @@ __global__ void __launch_bounds__(128) env_kernel(const __grid_constant__ Params
         s.node(i)[A_SP] = make_double2(-pd * p.inv_base, -qd * p.inv_base);
       }
       __syncwarp();
-      if (MODE == MODE_STEP) {
-        // prefetch the next profile row (reference _set_demand_and_pv :491-513: t = self.steps before the
-        // increment) into the scratch region with LDGSTS; it lands while the Newton iteration runs
-        long long nrow = start + steps_old;
-        if (nrow > p.n_rows - 1) nrow = p.n_rows - 1;
-        for (int j = gl; j < ng; j += G) cp_async8(next_row + j, p.prof_pv + nrow * ng + j);
-        for (int l = gl; l < nl; l += G) {
-          cp_async8(next_row + ng + l, p.prof_lp + nrow * nl + l);
-          cp_async8(next_row + ng + nl + l, p.prof_lq + nrow * nl + l);
-        }
-      }
+      if (MODE == MODE_STEP) named_bar_arrive(1, blockDim.x);   // the current rows are consumed: the helper may overwrite them
 
       // ---------------- Newton-Raphson ----------------
       PROF(1)
@@ -574,7 +609,6 @@ __global__ void __launch_bounds__(128) env_kernel(const __grid_constant__ Params
         nd[A_SP] = make_double2(-p.res_p[eN + b] * p.inv_base, -p.res_q[eN + b] * p.inv_base);
       }
     }
-    if (MODE == MODE_STEP) cp_async_wait_all();
     __syncwarp();
     const bool write_res = valid && (MODE != MODE_STEP || conv);
 
@@ -605,33 +639,11 @@ __global__ void __launch_bounds__(128) env_kernel(const __grid_constant__ Params
         if (write_res) p.cur_q[eG + j] = q_eff;
       }
     }
-    // next profile row + |N(0,1)| * std noise. Elements [pv | load_p | load_q] are drawn in Box-Muller
-    // pairs (2m, 2m+1); the base values were prefetched into `next_row`.
+    // the helper warp has drawn the next profile row meanwhile: take over the new sgen.p_mw (Appendix B.3: the
+    // observation mixes this solve's bus results with the NEXT row's PV)
     if (MODE == MODE_STEP) {
-      const uint32_t c1 = static_cast<uint32_t>(steps_old);
-      const int n_elem = ng + 2 * nl;
-#pragma unroll 2
-      for (int m = gl; 2 * m < n_elem; m += G) {
-        double z[2] = {0.0, 0.0};
-        if (p.add_noise) half_normal_pair(key, c1, m, z[0], z[1]);
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int el = 2 * m + u;
-          if (el >= n_elem) break;
-          const double base_v = next_row[el];
-          if (el < ng) {
-            const double pv = base_v + __ldg(p.pv_std + el) * z[u];
-            s.pv[el] = pv;
-            if (valid) p.cur_pv[eG + el] = pv;
-          } else if (el < ng + nl) {
-            const int l = el - ng;
-            if (valid) p.cur_pl[eL + l] = base_v + __ldg(p.lp_std + l) * z[u];
-          } else {
-            const int l = el - ng - nl;
-            if (valid) p.cur_ql[eL + l] = base_v + __ldg(p.lq_std + l) * z[u];
-          }
-        }
-      }
+      named_bar_sync(2, blockDim.x);
+      for (int j = gl; j < ng; j += G) s.pv[j] = next_row[j];
     }
     __syncwarp();
     PROF(8)

@@ -221,7 +221,7 @@ mapdn_status launch_env_kernel(mapdn_env* e, int mode, Params& p, cudaStream_t s
   cudaMemset(d_prof, 0, 12 * sizeof(long long));
   p.prof = d_prof;
 #endif
-  fn<<<grid, e->threads, e->smem, st>>>(p);
+  fn<<<grid, e->threads + (mode == MODE_STEP ? 32 : 0), e->smem, st>>>(p);   // MODE_STEP: + 1 helper warp
   MAPDN_CUDA(cudaGetLastError());
   e->launches++;
 #ifdef MAPDN_PROFILE
@@ -660,7 +660,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   }
   {
     int per_sm = 0;
-    TRY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel_for(G, MODE_STEP), e->threads, e->smem));
+    TRY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel_for(G, MODE_STEP), e->threads + 32, e->smem));
     e->max_blocks = std::max(1, per_sm) * dp.multiProcessorCount;
   }
 
