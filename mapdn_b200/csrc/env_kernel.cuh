@@ -286,7 +286,7 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
         return o;
       };
       uint64_t ed = h.esched[gl];
-      uint64_t ed_next = h.esched[min(1, p.n_esteps - 1) * G + gl];
+      uint64_t ed_next = h.esched[max(0, min(1, p.n_esteps - 1)) * G + gl];
       Own own = load_own(ed);
       double2 s01 = make_double2(0.0, 0.0), s23 = s01, tt = s01;     // Schur update produced by this lane's last step
       for (int st = 0; st < p.n_esteps; ++st) {
@@ -348,11 +348,11 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
         return o;
       };
       uint64_t bd = h.bsched[gl];
-      uint64_t bd_next = h.bsched[min(1, p.n_bsteps - 1) * G + gl];
+      uint64_t bd_next = h.bsched[max(0, min(1, p.n_bsteps - 1)) * G + gl];
       OwnB own = load_own(bd);
       double2 xl = make_double2(0.0, 0.0);               // dx of the node this lane solved in the previous step
       for (int st = 0; st < p.n_bsteps; ++st) {
-        const uint64_t bd_next2 = h.bsched[min(st + 2, p.n_bsteps - 1) * G + gl];
+        const uint64_t bd_next2 = h.bsched[max(0, min(st + 2, p.n_bsteps - 1)) * G + gl];
         const OwnB own_next = load_own(bd_next);         // D^-1 J and D^-1 r are final since the forward sweep
         double2* nd = s.node(static_cast<int>(bd & 0xFFFFu));
         __syncwarp();                                    // the previous step's dx are visible

@@ -61,3 +61,42 @@ def test_no_oracle_import_in_product():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_create_validates_arguments_without_touching_the_gpu(built_lib):
+    """Argument checks of mapdn_create run before any CUDA call: bad descriptions are refused with
+    MAPDN_ERR_INVALID (1) and a message, also on a box without a GPU."""
+    import ctypes as C
+    import numpy as np
+    from mapdn_b200 import _capi, cases
+    L = _capi.lib()
+    net = cases.case33()
+    cfg = _capi.CfgC(batch=4, barrier=0, voltage_weight=1.0, q_weight=0.1, v_upper=1.05, v_lower=0.95, episode_limit=240,
+                     action_low=-0.8, action_high=0.8, reset_action=1)
+    h = C.c_void_p()
+
+    def create(nd, c):
+        return L.mapdn_create(C.byref(nd), None, C.byref(c), 0, C.byref(h))
+
+    nd, keep = _capi.make_net_desc(net)
+    nd.n_bus = 1
+    assert create(nd, cfg) == 1 and b"n_bus" in L.mapdn_last_error()
+    nd, keep = _capi.make_net_desc(net)
+    nd.slack_bus = 99
+    assert create(nd, cfg) == 1 and b"slack_bus" in L.mapdn_last_error()
+    nd, keep = _capi.make_net_desc(net)
+    bad = net.br_to.copy(); bad[3] = 1000
+    nd.br_to = bad.ctypes.data_as(C.POINTER(C.c_int32))
+    assert create(nd, cfg) == 1 and b"branch endpoint" in L.mapdn_last_error()
+    nd, keep = _capi.make_net_desc(net)
+    cfg2 = _capi.CfgC.from_buffer_copy(cfg); cfg2.barrier = 9
+    assert create(nd, cfg2) == 1 and b"barrier" in L.mapdn_last_error()
+    cfg3 = _capi.CfgC.from_buffer_copy(cfg); cfg3.lanes_per_env = 5
+    assert create(nd, cfg3) == 1 and b"lanes_per_env" in L.mapdn_last_error()
+    cfg4 = _capi.CfgC.from_buffer_copy(cfg); cfg4.batch = 0
+    assert create(nd, cfg4) == 1
+    assert L.mapdn_create(None, None, C.byref(cfg), 0, C.byref(h)) == 1
+    assert not h.value
+    # null handles are refused, not dereferenced
+    assert L.mapdn_step(None, None, 0, None, None, None, None, None) == 1
+    assert L.mapdn_destroy(None) == 0

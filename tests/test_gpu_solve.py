@@ -141,3 +141,38 @@ def test_topology_errors():
     island = NetDesc(br_from=[0, 2], br_to=[1, 3], br_r=[.01] * 2, br_x=[.01] * 2, **base)
     with pytest.raises(MapdnError, match="not connected"):
         _env(island)
+
+
+def test_degenerate_topologies():
+    """2-bus net, a star (every PQ bus adjacent to the slack: forests of single-bus trees, no back sweep) and a
+    pure chain, against the oracle."""
+    from oracle.pandapower_nr import PandapowerEquivalent
+    rng = np.random.default_rng(5)
+    nets = []
+    nets.append(NetDesc(base_mva=1.0, n_bus=2, slack_bus=1, slack_vm=1.01, br_from=[0], br_to=[1], br_r=[0.01], br_x=[0.02],
+                        load_bus=[0], sgen_bus=[0], sgen_zone=[1], bus_zone=[1, 0]))
+    n = 9
+    nets.append(NetDesc(base_mva=1.0, n_bus=n, slack_bus=4, slack_vm=1.0, br_from=[4] * (n - 1),
+                        br_to=[b for b in range(n) if b != 4], br_r=rng.uniform(0.005, 0.02, n - 1),
+                        br_x=rng.uniform(0.005, 0.02, n - 1), load_bus=np.arange(n), sgen_bus=[0, 8], sgen_zone=[1, 2],
+                        bus_zone=[1, 1, 1, 1, 0, 2, 2, 2, 2]))
+    n = 40
+    nets.append(NetDesc(base_mva=1.0, n_bus=n, slack_bus=0, slack_vm=1.0, br_from=np.arange(n - 1), br_to=np.arange(1, n),
+                        br_r=rng.uniform(0.001, 0.004, n - 1), br_x=rng.uniform(0.001, 0.004, n - 1),
+                        load_bus=np.arange(1, n), sgen_bus=[n - 1, n // 2], sgen_zone=[1, 1], bus_zone=[0] + [1] * (n - 1)))
+    for net in nets:
+        for lanes in (0, 4, 32):
+            env = _env(net, lanes_per_env=lanes)
+            B = 5
+            pl = rng.uniform(0.0, 0.05, (B, net.n_load)); ql = 0.3 * pl
+            pv = rng.uniform(0.0, 0.2, (B, net.n_sgen)); q = rng.uniform(-0.05, 0.05, (B, net.n_sgen))
+            out = env.solve(pl, ql, pv, q)
+            pf = PandapowerEquivalent(net)
+            for e in range(B):
+                r = pf.runpp(pl[e], ql[e], pv[e], q[e])
+                assert r.converged and bool(out["converged"][e]) and int(out["iterations"][e]) == r.iterations
+                assert np.abs(out["vm"][e].cpu().numpy() - r.vm_pu).max() < VTOL
+                assert np.abs(out["va_deg"][e].cpu().numpy() - r.va_degree).max() < 1e-8
+                assert np.abs(out["p_bus"][e].cpu().numpy() - r.p_mw).max() < 1e-8
+                assert np.abs(out["pl"][e].cpu().numpy() - r.pl_mw).max() < 1e-9
+            env.close()
