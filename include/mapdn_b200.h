@@ -34,7 +34,7 @@ typedef enum {
   MAPDN_OK = 0,
   MAPDN_ERR_INVALID = 1,      /* bad argument / inconsistent description               */
   MAPDN_ERR_CUDA = 2,         /* CUDA runtime failure (text in mapdn_last_error)       */
-  MAPDN_ERR_TOPOLOGY = 3,     /* network not connected, or meshed (radial nets only)   */
+  MAPDN_ERR_TOPOLOGY = 3,     /* not connected, or meshed with more than 256 PQ buses  */
   MAPDN_ERR_UNSUPPORTED = 4,  /* feature of the reference not implemented              */
   MAPDN_ERR_NOMEM = 5
 } mapdn_status;

@@ -176,6 +176,8 @@ struct Hot {
   const uint64_t *ndesc, *esched, *bsched;
   const uint16_t *lptr, *lidx, *sptr, *sidx, *xptr, *xidx, *node_of_bus, *obs_off, *line_nodes;
   const double* line_c;
+  const uint16_t *nbr_ptr, *nbr_idx;   // meshed nets (dense solver) only
+  const double2* nbr_y;
 };
 struct Slab {
   double2* nodes;   // (npq + 1) records of kNodeArrays2 double2
@@ -388,13 +390,120 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
   return done;
 }
 
+// ------------------------------------------------------------------------------------------
+// Fallback for meshed networks: the same Newton-Raphson (same unknowns, same iterates up to rounding),
+// but the Jacobian is assembled dense ([2 npq] x [2 npq], row-major, unknown 2i = dtheta_i, 2i+1 = dV_i/V_i)
+// in a global-memory workspace and solved by one warp with partial-pivoting LU (what SuperLU does for
+// pandapower). O(npq^3) per solve: meant for small meshed feeders, not for the radial hot path.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool nr_solve_dense(const Params& p, const Hot& h, const Slab& s, double* __restrict__ ws,
+                                               int lane, bool skip, int& iters) {
+  const int npq = p.npq, m = 2 * npq, ld = m + 1;       // column m holds the right-hand side
+  for (int i = lane; i <= npq + 1; i += 32) {
+    const bool sl = (i == npq);
+    double2* nd = s.node(i);
+    nd[A_VV] = sl ? make_double2(p.vm0, p.va0) : make_double2(p.vm_init, 0.0);
+    nd[A_EF] = sl ? make_double2(p.e0, p.f0) : make_double2(p.vm_init, 0.0);
+    nd[A_UP] = make_double2(0.0, 0.0); nd[A_DN] = make_double2(0.0, 0.0); nd[A_T] = make_double2(0.0, 0.0);
+    nd[A_R] = make_double2(0.0, 0.0);
+  }
+  __syncwarp();
+  bool done = skip;
+  int it = 0;
+  iters = 0;
+  const double2 v0 = make_double2(p.e0, p.f0);
+  while (true) {
+    for (int idx = lane; idx < m * ld; idx += 32) ws[idx] = 0.0;
+    __syncwarp();
+    // mismatch + Jacobian rows of bus i (SURVEY A.4 formulas, unknown dV/V)
+    double nrm = 0.0;
+    for (int i = lane; i < npq; i += 32) {
+      const double2 vi = s.node(i)[A_EF];
+      const double2 ys = h.ysl[i], yi = h.yii[i], sp = s.node(i)[A_SP];
+      const double cs0 = vi.x * v0.x + vi.y * v0.y, sn0 = vi.y * v0.x - vi.x * v0.y;
+      double sa = ys.x * sn0 - ys.y * cs0, sb = ys.x * cs0 + ys.y * sn0;
+      double* rp = ws + static_cast<size_t>(2 * i) * ld;
+      double* rq = rp + ld;
+      for (int t = h.nbr_ptr[i], te = h.nbr_ptr[i + 1]; t < te; ++t) {
+        const int j = h.nbr_idx[t];
+        const double2 y = h.nbr_y[t], vj = s.node(j)[A_EF];
+        const double cc = vi.x * vj.x + vi.y * vj.y, ss = vi.y * vj.x - vi.x * vj.y;
+        const double a = y.x * ss - y.y * cc, b = y.x * cc + y.y * ss;
+        sa += a; sb += b;
+        rp[2 * j] = a; rp[2 * j + 1] = b; rq[2 * j] = -b; rq[2 * j + 1] = a;
+      }
+      const double vv = vi.x * vi.x + vi.y * vi.y;
+      const double gv = yi.x * vv, bv = yi.y * vv;
+      const double P = gv + sb, Q = sa - bv;
+      const double Fp = P - sp.x, Fq = Q - sp.y;
+      rp[2 * i] = -Q - bv; rp[2 * i + 1] = P + gv; rq[2 * i] = P - gv; rq[2 * i + 1] = Q - bv;
+      rp[m] = -Fp; rq[m] = -Fq;
+      nrm = nanmax(nrm, nanmax(fabs(Fp), fabs(Fq)));
+    }
+    const bool ok = __all_sync(kFull, nrm < p.tol);
+    if (!done && ok) { done = true; iters = it; }
+    if (done || it >= p.max_iter) break;
+    ++it;
+    __syncwarp();
+    // LU with partial pivoting, right-looking, rhs carried as column m
+    bool singular = false;
+    for (int k = 0; k < m; ++k) {
+      double best = -1.0; int brow = k;
+      for (int r = k + lane; r < m; r += 32) { const double v = fabs(ws[static_cast<size_t>(r) * ld + k]); if (v > best) { best = v; brow = r; } }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        const double ob = __shfl_xor_sync(kFull, best, o); const int orow = __shfl_xor_sync(kFull, brow, o);
+        if (ob > best || (ob == best && orow < brow)) { best = ob; brow = orow; }
+      }
+      if (!(best > 0.0)) { singular = true; break; }
+      if (brow != k)
+        for (int c = k + lane; c <= m; c += 32) {
+          const double t0 = ws[static_cast<size_t>(k) * ld + c];
+          ws[static_cast<size_t>(k) * ld + c] = ws[static_cast<size_t>(brow) * ld + c];
+          ws[static_cast<size_t>(brow) * ld + c] = t0;
+        }
+      __syncwarp();
+      const double pinv = 1.0 / ws[static_cast<size_t>(k) * ld + k];
+      for (int r = k + 1; r < m; ++r) {
+        const double l = ws[static_cast<size_t>(r) * ld + k] * pinv;     // same value in every lane (broadcast load)
+        if (l != 0.0)
+          for (int c = k + 1 + lane; c <= m; c += 32) ws[static_cast<size_t>(r) * ld + c] -= l * ws[static_cast<size_t>(k) * ld + c];
+      }
+      __syncwarp();
+    }
+    if (singular) { done = false; break; }
+    // back substitution; dx of bus i goes to its record (R)
+    for (int k = m - 1; k >= 0; --k) {
+      double acc = 0.0;
+      for (int c = k + 1 + lane; c < m; c += 32) acc += ws[static_cast<size_t>(k) * ld + c] * ws[static_cast<size_t>(c) * ld + m];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+      if (lane == 0) ws[static_cast<size_t>(k) * ld + m] = (ws[static_cast<size_t>(k) * ld + m] - acc) / ws[static_cast<size_t>(k) * ld + k];
+      __syncwarp();
+    }
+    for (int i = lane; i < npq; i += 32) {
+      double2* nd = s.node(i);
+      double2 v = nd[A_VV];
+      v.y += ws[static_cast<size_t>(2 * i) * ld + m];
+      v.x += v.x * ws[static_cast<size_t>(2 * i + 1) * ld + m];
+      double sn, cs;
+      sincos_angle(v.y, &sn, &cs);
+      nd[A_VV] = v;
+      nd[A_EF] = make_double2(v.x * cs, v.x * sn);
+    }
+    __syncwarp();
+  }
+  return done;
+}
+
 // sgen.q_mvar from an action: reference _clip_reactive_power :568-572
 __device__ __forceinline__ double clip_q(double a, double pv, double smax) {
   return sqrt(smax * smax - pv * pv) * a;
 }
 
-template <int G, int MODE>
+template <int G, int MODE, bool DENSE = false>
 __global__ void __launch_bounds__(160) env_kernel(const __grid_constant__ Params p) {
+  static_assert(!DENSE || G == 32, "the dense fallback uses one warp per env");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t stage_bar;
   PROF_DECL
@@ -420,6 +529,9 @@ __global__ void __launch_bounds__(160) env_kernel(const __grid_constant__ Params
   h.obs_off = reinterpret_cast<const uint16_t*>(smem_raw + hl.obs_off);
   h.line_nodes = reinterpret_cast<const uint16_t*>(smem_raw + hl.line_nodes);
   h.line_c = reinterpret_cast<const double*>(smem_raw + hl.line_c);
+  h.nbr_ptr = reinterpret_cast<const uint16_t*>(smem_raw + hl.nbr_ptr);
+  h.nbr_idx = reinterpret_cast<const uint16_t*>(smem_raw + hl.nbr_idx);
+  h.nbr_y = reinterpret_cast<const double2*>(smem_raw + hl.nbr_y);
 
   // MODE_STEP: the last warp of the CTA is a helper that draws the next profile rows (+ noise) of the CTA's
   // envs while the solver warps run the Newton iteration (the two only meet at two named barriers)
@@ -582,11 +694,16 @@ __global__ void __launch_bounds__(160) env_kernel(const __grid_constant__ Params
 
       // ---------------- Newton-Raphson ----------------
       PROF(1)
+      if (DENSE) {
+        double* ws = p.dense_ws + (static_cast<size_t>(blockIdx.x) * epb + gidx) * p.dense_stride;
+        conv = nr_solve_dense(p, h, s, ws, gl, !valid, iters);
+      } else {
 #ifdef MAPDN_PROFILE
-      conv = nr_solve<G>(p, h, s, gl, !valid, iters, _acc, _pt);
+        conv = nr_solve<G>(p, h, s, gl, !valid, iters, _acc, _pt);
 #else
-      conv = nr_solve<G>(p, h, s, gl, !valid, iters);
+        conv = nr_solve<G>(p, h, s, gl, !valid, iters);
 #endif
+      }
       PROF(4)
       if (MODE != MODE_RESET) break;
       if (conv) solved = true;

@@ -45,6 +45,8 @@ struct HotLayout {        // byte offsets inside the hot static blob (staged int
   int obs_off;            // uint16 [n_sgen*obs_dim]: obs entry -> double offset inside the env slab
   int line_nodes;         // uint16 [2*n_line]: from / to node of every line (npq = slack)
   int line_c;             // double [4*n_line]: loss coefficients (see mapdn_b200.cu)
+  int nbr_ptr, nbr_idx;   // meshed nets only: uint16 CSR of the PQ-PQ Ybus pattern ([npq+1], [nnz])
+  int nbr_y;              // meshed nets only: double2 [nnz]: Y[i,j] (G, B) of each CSR entry
   int bytes;              // total, multiple of 16
 };
 
@@ -89,6 +91,8 @@ struct Params {
   double* out_vm; double* out_va; double* out_p; double* out_q; double* out_pl;
   int* out_iters; unsigned char* out_conv;
   double* reward; unsigned char* term; double* info; double* obs; double* state;
+  double* dense_ws;       // meshed nets only: per resident env group, (2 npq) x (2 npq + 1) doubles [J | rhs]
+  int dense_stride;       // doubles per group in dense_ws
   long long* prof;        // MAPDN_PROFILE builds: per-phase clock64 totals of warp 0 of block 0
 };
 

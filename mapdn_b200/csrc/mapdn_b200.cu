@@ -142,6 +142,7 @@ struct mapdn_env {
   Params base{};                       // static + state pointers; io fields filled per call
   std::vector<void*> allocs;           // everything cudaMalloc'ed
   int G = 8, threads = 128, epb = 16, smem = 0, max_blocks = 0;
+  bool dense = false;                  // meshed net: dense-LU fallback solver
   long long launches = 0;
   // Ybus pieces kept for the test hook
   std::vector<double> ybr, ydiag;
@@ -191,7 +192,14 @@ KernelFn kernel_for_mode(int mode) {
   }
 }
 
-KernelFn kernel_for(int G, int mode) {
+KernelFn kernel_for(int G, int mode, bool dense = false) {
+  if (dense) {
+    switch (mode) {
+      case MODE_SOLVE: return env_kernel<32, MODE_SOLVE, true>;
+      case MODE_STEP: return env_kernel<32, MODE_STEP, true>;
+      default: return env_kernel<32, MODE_RESET, true>;
+    }
+  }
   switch (G) {
     case 4: return kernel_for_mode<4>(mode);
     case 8: return kernel_for_mode<8>(mode);
@@ -210,7 +218,7 @@ int env_stride2_for(int npq, int ng, int nl, int G) {
 }
 
 mapdn_status launch_env_kernel(mapdn_env* e, int mode, Params& p, cudaStream_t st) {
-  KernelFn fn = kernel_for(e->G, mode);
+  KernelFn fn = kernel_for(e->G, mode, e->dense);
   const int needed = (p.nb + e->epb - 1) / e->epb;
   int grid = std::min(needed, std::max(1, e->max_blocks));
   const int rounds = (needed + grid - 1) / grid;
@@ -357,10 +365,13 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     if (static_cast<int>(q.size()) != n)
       return bail(fail(MAPDN_ERR_TOPOLOGY, "network is not connected to the slack bus (" +
                                                std::to_string(n - q.size()) + " unreachable buses)"));
-    if (static_cast<int>(pairs.size()) != n - 1)
-      return bail(fail(MAPDN_ERR_TOPOLOGY, "network is meshed (" + std::to_string(pairs.size() - (n - 1)) +
-                                               " loop-closing branches); only radial feeders are supported"));
   }
+  // A radial net (|edges| = n - 1) takes the zero-fill tree solver; a meshed one the dense-LU fallback.
+  const bool meshed = static_cast<int>(pairs.size()) != n - 1;
+  if (meshed && n - 1 > 256)
+    return bail(fail(MAPDN_ERR_TOPOLOGY, "network is meshed (" + std::to_string(pairs.size() - (n - 1)) +
+                                             " loop-closing branches) and has more than 256 PQ buses: the dense "
+                                             "fallback solver only covers small meshed feeders"));
   const int npq = n - 1;
   // BFS inside the PQ forest (never crossing the slack bus)
   auto bfs = [&](int src, std::vector<int>& dist, std::vector<int>& from) {
@@ -402,6 +413,11 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   std::vector<int> parent(npq, -1), nchild(npq, 0), height(npq, 0);
   for (int i = 0; i < npq; ++i)
     if (parent_bus[order[i]] >= 0) { parent[i] = node_of_bus[parent_bus[order[i]]]; nchild[parent[i]]++; }
+  if (meshed) {   // no elimination forest: every bus is its own root, the sweeps are not used
+    std::fill(parent.begin(), parent.end(), -1);
+    std::fill(nchild.begin(), nchild.end(), 0);
+    for (int b = 0; b < n; ++b) depth[b] = 0;
+  }
   for (int i = npq - 1; i >= 0; --i)
     if (parent[i] >= 0) height[parent[i]] = std::max(height[parent[i]], height[i] + 1);
   std::vector<int> cfirst(npq + 1);
@@ -427,7 +443,8 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   for (int l = 0; l < n_lev; ++l) max_width = std::max(max_width, elev[l + 1] - elev[l]);
   for (int i = 0; i < npq; ++i) max_children = std::max(max_children, nchild[i]);
   int G = cfg->lanes_per_env;
-  if (G == 0) G = (npq <= 64) ? 8 : 32;     // measured on B200: 8 lanes/env for 33-bus feeders, a full warp beyond
+  if (G == 0) G = (npq <= 64) ? 8 : 32;
+  if (meshed) G = 32;                    // the dense fallback works one warp per env     // measured on B200: 8 lanes/env for 33-bus feeders, a full warp beyond
   // Flat schedules for this G: a level wider than G takes several steps; idle lanes get the trash record.
   // Lanes follow chains: a bus is placed on the lane that handled its child (forward sweep) / its parent
   // (back sweep) in the immediately preceding step whenever that lane is free, so the dependent value can
@@ -583,6 +600,22 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   }
   const int n_line = static_cast<int>(line_nodes.size() / 2);
 
+  // PQ-PQ Ybus pattern (CSR) for the dense fallback
+  std::vector<uint16_t> nbr_ptr(1, 0), nbr_idx;
+  std::vector<double> nbr_y;
+  if (meshed) {
+    nbr_ptr.assign(npq + 1, 0);
+    for (int i = 0; i < npq; ++i) {
+      const int b = order[i];
+      for (int v : adj[b]) {
+        if (v == slack) continue;
+        double g, bb;
+        yoff(b, v, g, bb);
+        nbr_idx.push_back(static_cast<uint16_t>(node_of_bus[v])); nbr_y.push_back(g); nbr_y.push_back(bb);
+      }
+      nbr_ptr[i + 1] = static_cast<uint16_t>(nbr_idx.size());
+    }
+  }
   // ---- 3b. hot static blob ----
   HotLayout hl{};
   {
@@ -595,6 +628,8 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     hl.xptr = take(2 * xptr.size()); hl.xidx = take(2 * std::max<size_t>(1, xidx.size()));
     hl.node_of_bus = take(2 * n); hl.obs_off = take(2 * obs_off.size());
     hl.line_nodes = take(2 * std::max<size_t>(1, line_nodes.size())); hl.line_c = take(8 * std::max<size_t>(1, line_c.size()));
+    hl.nbr_ptr = take(2 * nbr_ptr.size()); hl.nbr_idx = take(2 * std::max<size_t>(1, nbr_idx.size()));
+    hl.nbr_y = take(8 * std::max<size_t>(2, nbr_y.size()));
     hl.bytes = off;
   }
   std::vector<unsigned char> hot(hl.bytes, 0);
@@ -634,6 +669,11 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     uint16_t* nob = reinterpret_cast<uint16_t*>(hot.data() + hl.node_of_bus);
     for (int b = 0; b < n; ++b) nob[b] = static_cast<uint16_t>(node_of_bus[b]);
     std::memcpy(hot.data() + hl.obs_off, obs_off.data(), 2 * obs_off.size());
+    std::memcpy(hot.data() + hl.nbr_ptr, nbr_ptr.data(), 2 * nbr_ptr.size());
+    if (!nbr_idx.empty()) {
+      std::memcpy(hot.data() + hl.nbr_idx, nbr_idx.data(), 2 * nbr_idx.size());
+      std::memcpy(hot.data() + hl.nbr_y, nbr_y.data(), 8 * nbr_y.size());
+    }
     if (n_line) {
       std::memcpy(hot.data() + hl.line_nodes, line_nodes.data(), 2 * line_nodes.size());
       std::memcpy(hot.data() + hl.line_c, line_c.data(), 8 * line_c.size());
@@ -653,15 +693,17 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   if (smem_for(warps) > max_smem)
     return bail(fail(MAPDN_ERR_UNSUPPORTED, "network too large for the shared-memory resident solver (" +
                                                 std::to_string(smem_for(warps)) + " B needed)"));
+  e->dense = meshed;
   e->G = G; e->threads = 32 * warps; e->epb = warps * (32 / G); e->smem = static_cast<int>(smem_for(warps));
   for (int mode = 0; mode < 3; ++mode) {
-    KernelFn fn = kernel_for(G, mode);
+    KernelFn fn = kernel_for(G, mode, meshed);
     TRY_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem));
   }
   {
     int per_sm = 0;
-    TRY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel_for(G, MODE_STEP), e->threads + 32, e->smem));
+    TRY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel_for(G, MODE_STEP, meshed), e->threads + 32, e->smem));
     e->max_blocks = std::max(1, per_sm) * dp.multiProcessorCount;
+    if (meshed) e->max_blocks = std::min(e->max_blocks, 2 * dp.multiProcessorCount);   // bounds the dense workspace
   }
 
   // ---- 6. upload + env state ----
@@ -720,6 +762,12 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   TRY(dev_alloc(e, B * std::max(1, n_line), &P.res_pl));
   TRY(dev_alloc(e, B, &P.steps)); TRY(dev_alloc(e, B, &P.sum_rewards));
   TRY(dev_alloc(e, B, &P.start_row)); TRY(dev_alloc(e, B, &P.episode));
+  if (meshed) {
+    const size_t m = 2 * static_cast<size_t>(npq);
+    P.dense_stride = static_cast<int>(m * (m + 1));
+    const size_t groups = static_cast<size_t>(e->max_blocks) * e->epb;       // one slice per resident env group
+    TRY(dev_alloc(e, groups * P.dense_stride, &P.dense_ws));
+  }
   // staging for the *_host entry points
   TRY(dev_alloc(e, B * ng, &e->d_stage_actions)); TRY(dev_alloc(e, B, &e->d_stage_reward)); TRY(dev_alloc(e, B, &e->d_stage_term));
   TRY(dev_alloc(e, B * MAPDN_N_INFO, &e->d_stage_info)); TRY(dev_alloc(e, B * ng * obs_dim, &e->d_stage_obs));

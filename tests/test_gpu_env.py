@@ -266,3 +266,20 @@ def test_shim_history_and_reset_time():
     assert (env._episode_start_day, env._episode_start_hour, env._episode_start_interval) == start
     env.reset()
     env.close()
+
+
+def test_meshed_env_trajectory_matches_oracle():
+    """Full env step (reward / obs / next row / divergence-free path) on a meshed feeder = dense fallback solver."""
+    from oracle.voltage_control_ref import VoltageControlOracle
+    from test_gpu_solve import _case33_meshed
+    net, prof = _case33_meshed(), cases.make_profiles("case33", n_days=4)
+    env = _make(net, prof, dict(voltage_barrier_type="bowl", seed=6), batch=7)
+    ids = [0, 3, 6]
+    oracles = [VoltageControlOracle(net, prof, env.args, env_id=i) for i in ids]
+    obs, state = env.reset()
+    for o, i in zip(oracles, ids):
+        oo, os_ = o.reset()
+        assert np.abs(np.array(oo) - obs[i].cpu().numpy()).max() < TOL and np.abs(os_ - state[i].cpu().numpy()).max() < 1e-8
+    rng = np.random.default_rng(1)
+    for t in range(3):
+        _cmp_step(env, oracles, ids, rng.uniform(-0.8, 0.8, (7, 6)))

@@ -131,16 +131,54 @@ def test_divergence_is_flagged_per_env():
     assert np.abs(out["vm"][0].cpu().numpy() - out["vm"][2].cpu().numpy()).max() == 0.0
 
 
+def _case33_meshed():
+    """IEEE 33-bus with its five tie lines closed (Baran & Wu): a weakly meshed feeder."""
+    net = cases.case33()
+    zb = 12.66 ** 2
+    ties = [(8, 21, 2.0, 2.0), (9, 15, 2.0, 2.0), (12, 22, 2.0, 2.0), (18, 33, 0.5, 0.5), (25, 29, 0.5, 0.5)]
+    f = np.r_[net.br_from, [t[0] - 1 for t in ties]]; t = np.r_[net.br_to, [t[1] - 1 for t in ties]]
+    r = np.r_[net.br_r, [t[2] / zb for t in ties]]; x = np.r_[net.br_x, [t[3] / zb for t in ties]]
+    return NetDesc(base_mva=1.0, n_bus=33, slack_bus=0, slack_vm=1.0, br_from=f, br_to=t, br_r=r, br_x=x,
+                   load_bus=net.load_bus, sgen_bus=net.sgen_bus, sgen_zone=net.sgen_zone, bus_zone=net.bus_zone)
+
+
+def test_meshed_network_uses_the_dense_fallback():
+    """pandapower solves any topology; a meshed net takes the dense-LU Newton path: same iterates, same results."""
+    from oracle.pandapower_nr import PandapowerEquivalent
+    net = _case33_meshed()
+    inp = cases.synthetic_inputs("case33", 40, seed=12)
+    q = inp["action"] * np.sqrt(inp["s_max"] ** 2 - inp["p_pv"] ** 2)
+    env = _env(net, batch=1)
+    assert env.dims["lanes_per_env"] == 32
+    out = env.solve(inp["p_load"], inp["q_load"], inp["p_pv"], q)
+    pf = PandapowerEquivalent(net)
+    for e in range(40):
+        r = pf.runpp(inp["p_load"][e], inp["q_load"][e], inp["p_pv"][e], q[e])
+        assert r.converged and bool(out["converged"][e]) and int(out["iterations"][e]) == r.iterations
+        assert np.abs(out["vm"][e].cpu().numpy() - r.vm_pu).max() < VTOL
+        assert np.abs(out["va_deg"][e].cpu().numpy() - r.va_degree).max() < 1e-8
+        assert np.abs(out["p_bus"][e].cpu().numpy() - r.p_mw).max() < 1e-8
+        assert np.abs(out["pl"][e].cpu().numpy() - r.pl_mw).max() < 1e-9
+    # a small meshed square as well
+    sq = NetDesc(base_mva=1.0, n_bus=4, slack_bus=0, slack_vm=1.0, load_bus=[1, 2, 3], sgen_bus=[2], sgen_zone=[1],
+                 bus_zone=[0, 1, 1, 1], br_from=[0, 1, 2, 3], br_to=[1, 2, 3, 1], br_r=[.01] * 4, br_x=[.02] * 4)
+    o2 = _env(sq).solve(np.full((1, 3), 0.1), np.full((1, 3), 0.03), np.full((1, 1), 0.2), np.zeros((1, 1)))
+    r2 = PandapowerEquivalent(sq).runpp(np.full(3, 0.1), np.full(3, 0.03), [0.2], [0.0])
+    assert np.abs(o2["vm"][0].cpu().numpy() - r2.vm_pu).max() < VTOL
+
+
 def test_topology_errors():
     from mapdn_b200._capi import MapdnError
     base = dict(base_mva=1.0, n_bus=4, slack_bus=0, slack_vm=1.0, load_bus=[1], sgen_bus=[2], sgen_zone=[1],
                 bus_zone=[0, 1, 1, 1])
-    meshed = NetDesc(br_from=[0, 1, 2, 3], br_to=[1, 2, 3, 1], br_r=[.01] * 4, br_x=[.01] * 4, **base)
-    with pytest.raises(MapdnError, match="meshed"):
-        _env(meshed)
     island = NetDesc(br_from=[0, 2], br_to=[1, 3], br_r=[.01] * 2, br_x=[.01] * 2, **base)
     with pytest.raises(MapdnError, match="not connected"):
         _env(island)
+    n = 300                                              # a large ring: meshed and beyond the dense fallback
+    ring = NetDesc(base_mva=1.0, n_bus=n, slack_bus=0, slack_vm=1.0, br_from=np.arange(n), br_to=(np.arange(n) + 1) % n,
+                   br_r=[.001] * n, br_x=[.001] * n, load_bus=[1], sgen_bus=[2], sgen_zone=[1], bus_zone=[0] + [1] * (n - 1))
+    with pytest.raises(MapdnError, match="meshed"):
+        _env(ring)
 
 
 def test_degenerate_topologies():
