@@ -11,8 +11,8 @@ rep, kname = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "mapdn_b200", "libmapdn_b200.so")
-m = re.search(r"<\(int\)(\d+), \(int\)(\d+)>", kname)
-mangled = f"_ZN5mapdn10env_kernelILi{m.group(1)}ELi{m.group(2)}EEEvNS_6ParamsE"
+m = re.search(r"<\(int\)(\d+), \(int\)(\d+)(?:, \(bool\)(\d))?>", kname)
+mangled = f"_ZN5mapdn10env_kernelILi{m.group(1)}ELi{m.group(2)}ELb{m.group(3) or 0}EEEvNS_6ParamsE"
 with tempfile.TemporaryDirectory() as d:
     subprocess.check_call(["cuobjdump", "-xelf", "all", so], cwd=d, stdout=subprocess.DEVNULL)
     cub = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
