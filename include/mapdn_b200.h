@@ -138,7 +138,7 @@ typedef struct {
                               /* global env id so results do not depend on the sharding)*/
   double tol;                 /* NR tolerance on ||F||inf p.u. [1e-8]; <=0 => default   */
   int32_t max_iter;           /* NR iteration cap [10]; <=0 => default                  */
-  int32_t lanes_per_env;      /* 0 = auto; else 4, 8, 16 or 32 threads per env          */
+  int32_t lanes_per_env;      /* 0 = auto; else 4, 8, 16, 32, 64 or 128 threads per env */
 } mapdn_cfg;
 
 typedef struct {

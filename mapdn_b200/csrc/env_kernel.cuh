@@ -40,20 +40,69 @@ constexpr double kRad2Deg = 57.295779513082320876798;
 
 __device__ __forceinline__ double nanmax(double a, double b) { return (b > a || b != b) ? b : a; }
 
-template <int G> __device__ __forceinline__ double group_nanmax(double v) {
+// ---- group primitives. A group = the G threads that own one env: a sub-warp slice (G <= 32, all groups of
+//      a warp run in lock-step, synchronised with __syncwarp) or G/32 whole warps (G = 64 / 128, large feeders:
+//      synchronised with a named barrier per group; ids 3.. - 0 is __syncthreads, 1-2 the helper warp's) ----
+template <int G> __device__ __forceinline__ void grp_sync(int gidx) {
+  if constexpr (G <= 32) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" ::"r"(3 + gidx), "r"(G) : "memory");
+}
+// true iff `pred` holds on every thread of the group (includes a group barrier when G > 32)
+template <int G> __device__ __forceinline__ bool grp_all(int gidx, bool pred) {
+  if constexpr (G <= 32) {
+    const unsigned ok = __ballot_sync(kFull, pred);
+    const unsigned gmask = (G == 32) ? kFull : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+    return (ok & gmask) == gmask;
+  } else {
+    unsigned r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.u32 q, %1, 0;\n\t"
+        "bar.red.and.pred p, %2, %3, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(r)
+        : "r"(static_cast<unsigned>(pred)), "r"(3 + gidx), "r"(G)
+        : "memory");
+    return r != 0;
+  }
+}
+// loop-exit test of the lock-step sub-warp groups: every env handled by this warp is done (G <= 32);
+// for multi-warp groups the env's own flag decides (it is group-uniform)
+template <int G> __device__ __forceinline__ bool grp_exit(bool done) {
+  if constexpr (G <= 32) return __all_sync(kFull, done);
+  else return done;
+}
+template <int G> __device__ __forceinline__ double warp_part_sum(double v) {
 #pragma unroll
-  for (int m = G / 2; m >= 1; m >>= 1) v = nanmax(v, __shfl_xor_sync(kFull, v, m));
+  for (int m = (G < 32 ? G : 32) / 2; m >= 1; m >>= 1) v += __shfl_xor_sync(kFull, v, m);
   return v;
 }
-template <int G> __device__ __forceinline__ double group_sum(double v) {
+template <int G> __device__ __forceinline__ double warp_part_max(double v) {
 #pragma unroll
-  for (int m = G / 2; m >= 1; m >>= 1) v += __shfl_xor_sync(kFull, v, m);
+  for (int m = (G < 32 ? G : 32) / 2; m >= 1; m >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, m));
   return v;
 }
-template <int G> __device__ __forceinline__ double group_max(double v) {
+// sum / max over the group of NV values at once; `scratch` = >= NV * G/32 doubles of the env's slab (G > 32 only)
+template <int G, int NV> __device__ __forceinline__ void grp_reduce(int gidx, int gl, double (&v)[NV], const bool (&is_max)[NV],
+                                                                    double* scratch) {
 #pragma unroll
-  for (int m = G / 2; m >= 1; m >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, m));
-  return v;
+  for (int k = 0; k < NV; ++k) v[k] = is_max[k] ? warp_part_max<G>(v[k]) : warp_part_sum<G>(v[k]);
+  if constexpr (G > 32) {
+    constexpr int W = G / 32;
+    grp_sync<G>(gidx);                                   // scratch is free
+    if ((gl & 31) == 0) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) scratch[(gl >> 5) * NV + k] = v[k];
+    }
+    grp_sync<G>(gidx);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double a = scratch[k];
+#pragma unroll
+      for (int w = 1; w < W; ++w) a = is_max[k] ? fmax(a, scratch[w * NV + k]) : a + scratch[w * NV + k];
+      v[k] = a;
+    }
+  }
 }
 
 // Reciprocal without the library's special-case branch: MUFU.RCP64H seed (~2^-23 rel. error) + two
@@ -196,7 +245,7 @@ struct Slab {
 // Returns converged; `iters` = number of linear solves (pandapower's iteration count).
 // ------------------------------------------------------------------------------------------
 template <int G>
-__device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Slab& s, int gl, bool skip, int& iters
+__device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Slab& s, int gidx, int gl, bool skip, int& iters
 #ifdef MAPDN_PROFILE
     , long long* _acc, long long& _pt
 #endif
@@ -215,7 +264,7 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
     nd[A_R] = make_double2(0.0, 0.0);       // record npq is also the "no parent" slot of the back sweep
     if (i >= npq) { nd[A_D01] = make_double2(1.0, 0.0); nd[A_D23] = make_double2(0.0, 1.0); }
   }
-  __syncwarp();
+  grp_sync<G>(gidx);
 
   bool done = skip;      // this group's env converged (idle groups never hold the warp back)
   int it = 0;
@@ -235,7 +284,7 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
       nd[A_UP] = make_double2(yu.x * ss - yu.y * cc, yu.x * cc + yu.y * ss);
       nd[A_DN] = make_double2(-yd.x * ss - yd.y * cc, yd.x * cc - yd.y * ss);
     }
-    __syncwarp();
+    grp_sync<G>(gidx);
     PROF(3)
     // --- mismatch F = S_calc - S_spec and diagonal Jacobian blocks ---
     double nrm = 0.0;
@@ -266,14 +315,13 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
       nd[A_R] = make_double2(-Fp, -Fq);
       nrm = nanmax(nrm, nanmax(fabs(Fp), fabs(Fq)));
     }
-    {   // ||F||inf < tol for the whole env <=> every lane of the group is below tol (NaN-safe)
-      const unsigned ok = __ballot_sync(kFull, nrm < p.tol);
-      const unsigned gmask = (G == 32) ? kFull : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
-      if (!done && (ok & gmask) == gmask) { done = true; iters = it; }
+    {   // ||F||inf < tol for the whole env <=> every thread of the group is below tol (NaN-safe)
+      const bool ok = grp_all<G>(gidx, nrm < p.tol);
+      if (!done && ok) { done = true; iters = it; }
     }
-    if (__all_sync(kFull, done) || it >= p.max_iter) break;
+    if (grp_exit<G>(done) || it >= p.max_iter) break;
     ++it;
-    __syncwarp();
+    grp_sync<G>(gidx);
     PROF(4)
     // --- forward elimination, leaves first: a flat schedule of steps (a level of the elimination forest,
     //     split when it is wider than the group), one entry per (step, lane). Lanes follow chains of the
@@ -300,7 +348,7 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
         double2* nd = s.node(i);
         double2 d01 = own.d01, d23 = own.d23, r = own.r;
         const double2 u = own.u, d = own.d;   // J[i,p] = [[a,b],[-b,a]](u), J[p,i] likewise (d); zero at roots
-        __syncwarp();                                    // the previous step's Schur updates are visible
+        grp_sync<G>(gidx);                                    // the previous step's Schur updates are visible
         double2 p01 = s01, p23 = s23, pt = tt;           // child 0: registers ...
         if (!(fl & kEschedReg0)) { p01 = make_double2(0.0, 0.0); p23 = p01; pt = p01; }
         if (fl & kEschedLoad0) { const double2* k0 = s.node(c0); p01 = k0[A_UP]; p23 = k0[A_DN]; pt = k0[A_T]; }   // ... or smem
@@ -357,7 +405,7 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
         const uint64_t bd_next2 = h.bsched[max(0, min(st + 2, p.n_bsteps - 1)) * G + gl];
         const OwnB own_next = load_own(bd_next);         // D^-1 J and D^-1 r are final since the forward sweep
         double2* nd = s.node(static_cast<int>(bd & 0xFFFFu));
-        __syncwarp();                                    // the previous step's dx are visible
+        grp_sync<G>(gidx);                                    // the previous step's dx are visible
         double2 xp = xl;
         if (!((bd >> 32) & 1u)) xp = s.node(static_cast<int>((bd >> 16) & 0xFFFFu))[A_R];
         double2 x = own.x;
@@ -367,7 +415,7 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
         xl = x;
         bd = bd_next; bd_next = bd_next2; own = own_next;
       }
-      __syncwarp();
+      grp_sync<G>(gidx);
     }
     PROF(6)
     // --- update (theta += dtheta, V += V * dV/V) and V = Vm exp(j theta) ---
@@ -385,7 +433,7 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
         nd[A_EF] = make_double2(v.x * cs, v.x * sn);
       }
     }
-    __syncwarp();
+    grp_sync<G>(gidx);
   }
   return done;
 }
@@ -502,8 +550,9 @@ __device__ __forceinline__ double clip_q(double a, double pv, double smax) {
 }
 
 template <int G, int MODE, bool DENSE = false>
-__global__ void __launch_bounds__(160) env_kernel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(G > 32 ? 544 : 160) env_kernel(const __grid_constant__ Params p) {
   static_assert(!DENSE || G == 32, "the dense fallback uses one warp per env");
+  static_assert(G == 4 || G == 8 || G == 16 || G == 32 || G == 64 || G == 128, "unsupported group size");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t stage_bar;
   PROF_DECL
@@ -675,7 +724,7 @@ __global__ void __launch_bounds__(160) env_kernel(const __grid_constant__ Params
         stage_pl[l] = pl * sc; stage_ql[l] = ql * sc;
       }
       if (!hot_ready) { stage_hot_wait(&stage_bar); hot_ready = true; }
-      __syncwarp();
+      grp_sync<G>(gidx);
       // (2) A.1: PD/QD per bus, Sbus = -(PD + jQD)/baseMVA
       for (int i = gl; i < npq; i += G) {
         double pd = 0.0, qd = 0.0;
@@ -689,7 +738,7 @@ __global__ void __launch_bounds__(160) env_kernel(const __grid_constant__ Params
         }
         s.node(i)[A_SP] = make_double2(-pd * p.inv_base, -qd * p.inv_base);
       }
-      __syncwarp();
+      grp_sync<G>(gidx);
       if (MODE == MODE_STEP) named_bar_arrive(1, blockDim.x);   // the current rows are consumed: the helper may overwrite them
 
       // ---------------- Newton-Raphson ----------------
@@ -699,17 +748,17 @@ __global__ void __launch_bounds__(160) env_kernel(const __grid_constant__ Params
         conv = nr_solve_dense(p, h, s, ws, gl, !valid, iters);
       } else {
 #ifdef MAPDN_PROFILE
-        conv = nr_solve<G>(p, h, s, gl, !valid, iters, _acc, _pt);
+        conv = nr_solve<G>(p, h, s, gidx, gl, !valid, iters, _acc, _pt);
 #else
-        conv = nr_solve<G>(p, h, s, gl, !valid, iters);
+        conv = nr_solve<G>(p, h, s, gidx, gl, !valid, iters);
 #endif
       }
       PROF(4)
       if (MODE != MODE_RESET) break;
       if (conv) solved = true;
-      if (__all_sync(kFull, solved)) break;
+      if (grp_exit<G>(solved)) break;
       if (!solved) ++attempt;                       // re-draw this env (reference retry loop :108-133)
-      __syncwarp();
+      grp_sync<G>(gidx);
     }
 
     // ---------------- epilogue ----------------
@@ -726,7 +775,7 @@ __global__ void __launch_bounds__(160) env_kernel(const __grid_constant__ Params
         nd[A_SP] = make_double2(-p.res_p[eN + b] * p.inv_base, -p.res_q[eN + b] * p.inv_base);
       }
     }
-    __syncwarp();
+    grp_sync<G>(gidx);
     const bool write_res = valid && (MODE != MODE_STEP || conv);
 
     // slack injection (pfsoln): S0 = V0 conj(Ybus[0,:] V) -> sentinel record's SP
@@ -762,7 +811,7 @@ __global__ void __launch_bounds__(160) env_kernel(const __grid_constant__ Params
       named_bar_sync(2, blockDim.x);
       for (int j = gl; j < ng; j += G) s.pv[j] = next_row[j];
     }
-    __syncwarp();
+    grp_sync<G>(gidx);
     PROF(8)
     // res_bus columns per node (BP) and the "demand" columns of get_obs (OP = BP + sgens of the bus's own zone)
     for (int i = gl; i <= npq; i += G) {
@@ -774,7 +823,7 @@ __global__ void __launch_bounds__(160) env_kernel(const __grid_constant__ Params
       for (int t = h.xptr[i], te = h.xptr[i + 1]; t < te; ++t) { const int g = h.xidx[t]; op.x += s.pv[g]; op.y += s.q[g]; }
       nd[A_BP] = bp; nd[A_OP] = op;
     }
-    __syncwarp();
+    grp_sync<G>(gidx);
     // per-bus results + voltage statistics (reference _calc_reward :584-596, :610)
     double cnt_lo = 0, cnt_hi = 0, sum_dev = 0, sum_v = 0, max_drop = 0, max_rise = 0, sum_bar = 0;
     const double v_ref = 0.5 * (p.v_lower + p.v_upper);
@@ -826,15 +875,18 @@ __global__ void __launch_bounds__(160) env_kernel(const __grid_constant__ Params
         if (p.out_iters) p.out_iters[env] = conv ? iters : p.max_iter;
         if (p.out_conv) p.out_conv[env] = conv ? 1 : 0;
       }
-      __syncwarp();
+      grp_sync<G>(gidx);
       continue;
     }
 
     if (MODE == MODE_STEP) {
-      cnt_lo = group_sum<G>(cnt_lo); cnt_hi = group_sum<G>(cnt_hi);
-      sum_dev = group_sum<G>(sum_dev); sum_v = group_sum<G>(sum_v); sum_bar = group_sum<G>(sum_bar);
-      max_drop = group_max<G>(max_drop); max_rise = group_max<G>(max_rise);
-      sum_pl = group_sum<G>(sum_pl); sum_q_eff = group_sum<G>(sum_q_eff); sum_q_try = group_sum<G>(sum_q_try);
+      {
+        double rv[10] = {cnt_lo, cnt_hi, sum_dev, sum_v, sum_bar, max_drop, max_rise, sum_pl, sum_q_eff, sum_q_try};
+        const bool rmax[10] = {false, false, false, false, false, true, true, false, false, false};
+        grp_reduce<G, 10>(gidx, gl, rv, rmax, s.scratch);
+        cnt_lo = rv[0]; cnt_hi = rv[1]; sum_dev = rv[2]; sum_v = rv[3]; sum_bar = rv[4];
+        max_drop = rv[5]; max_rise = rv[6]; sum_pl = rv[7]; sum_q_eff = rv[8]; sum_q_try = rv[9];
+      }
       const double inv_n = 1.0 / n;
       const double pct = (cnt_lo + cnt_hi) * inv_n;
       const double q_loss = sum_q_eff / ng;
@@ -889,7 +941,7 @@ __global__ void __launch_bounds__(160) env_kernel(const __grid_constant__ Params
         if (valid) o[idx] = v;
       }
     }
-    __syncwarp();
+    grp_sync<G>(gidx);
     PROF(11)
   }
 #ifdef MAPDN_PROFILE

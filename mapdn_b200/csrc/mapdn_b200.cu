@@ -204,6 +204,8 @@ KernelFn kernel_for(int G, int mode, bool dense = false) {
     case 4: return kernel_for_mode<4>(mode);
     case 8: return kernel_for_mode<8>(mode);
     case 16: return kernel_for_mode<16>(mode);
+    case 64: return kernel_for_mode<64>(mode);
+    case 128: return kernel_for_mode<128>(mode);
     default: return kernel_for_mode<32>(mode);
   }
 }
@@ -278,9 +280,9 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   if (net->slack_bus < 0 || net->slack_bus >= n) return fail(MAPDN_ERR_INVALID, "slack_bus out of range");
   if (!(net->base_mva > 0)) return fail(MAPDN_ERR_INVALID, "base_mva must be positive");
   if (cfg->barrier < 0 || cfg->barrier > 4) return fail(MAPDN_ERR_INVALID, "unknown voltage barrier");
-  if (cfg->lanes_per_env != 0 && cfg->lanes_per_env != 4 && cfg->lanes_per_env != 8 &&
-      cfg->lanes_per_env != 16 && cfg->lanes_per_env != 32)
-    return fail(MAPDN_ERR_INVALID, "lanes_per_env must be 0, 4, 8, 16 or 32");
+  if (cfg->lanes_per_env != 0 && cfg->lanes_per_env != 4 && cfg->lanes_per_env != 8 && cfg->lanes_per_env != 16 &&
+      cfg->lanes_per_env != 32 && cfg->lanes_per_env != 64 && cfg->lanes_per_env != 128)
+    return fail(MAPDN_ERR_INVALID, "lanes_per_env must be 0, 4, 8, 16, 32, 64 or 128");
   for (int k = 0; k < nbr; ++k)
     if (net->br_from[k] < 0 || net->br_from[k] >= n || net->br_to[k] < 0 || net->br_to[k] >= n ||
         net->br_from[k] == net->br_to[k])
@@ -685,16 +687,19 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   TRY_CUDA(cudaGetDeviceProperties(&dp, device));
   const int stride2 = env_stride2_for(npq, ng, nl, G);
   const size_t max_smem = dp.sharedMemPerBlockOptin;
-  auto smem_for = [&](int w) { return static_cast<size_t>(hl.bytes) + static_cast<size_t>(w) * (32 / G) * stride2 * 16; };
-  int warps = 4;
-  // prefer enough CTAs to spread over all SMs
-  while (warps > 1 && (cfg->batch + warps * (32 / G) - 1) / (warps * (32 / G)) < 2 * dp.multiProcessorCount) warps /= 2;
-  while (warps > 1 && smem_for(warps) > max_smem) --warps;
-  if (smem_for(warps) > max_smem)
+  // envs per CTA: sub-warp groups pack 32/G envs into each of 1..4 solver warps; multi-warp groups (G = 64 / 128)
+  // put 1..4 envs of G threads in a CTA. Fewer envs per CTA when that spreads the batch over all SMs.
+  auto smem_for = [&](int epb) { return static_cast<size_t>(hl.bytes) + static_cast<size_t>(epb) * stride2 * 16; };
+  const int unit = (G <= 32) ? 32 / G : 1;               // envs added per step of the search
+  int epb = 4 * unit;
+  if (G > 32) while (epb > 1 && epb * G > 512) --epb;
+  while (epb > unit && (cfg->batch + epb - 1) / epb < 2 * dp.multiProcessorCount) epb = (G <= 32) ? epb / 2 : epb - 1;
+  while (epb > unit && smem_for(epb) > max_smem) epb -= unit;
+  if (smem_for(epb) > max_smem)
     return bail(fail(MAPDN_ERR_UNSUPPORTED, "network too large for the shared-memory resident solver (" +
-                                                std::to_string(smem_for(warps)) + " B needed)"));
+                                                std::to_string(smem_for(epb)) + " B needed)"));
   e->dense = meshed;
-  e->G = G; e->threads = 32 * warps; e->epb = warps * (32 / G); e->smem = static_cast<int>(smem_for(warps));
+  e->G = G; e->threads = epb * G; e->epb = epb; e->smem = static_cast<int>(smem_for(epb));
   for (int mode = 0; mode < 3; ++mode) {
     KernelFn fn = kernel_for(G, mode, meshed);
     TRY_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem));

@@ -6,7 +6,7 @@ from mapdn_b200.env import BatchedVoltageControl
 name = sys.argv[1] if len(sys.argv) > 1 else "case33"
 net, prof = cases.make_case(name), cases.make_profiles(name)
 for G in [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "8,16").split(",")]:
-    for B in (32 // G, 128, 1024, 4096, 16384, 65536, 262144):
+    for B in (max(1, 32 // G), 128, 1024, 4096, 16384, 65536, 262144):
         try:
             env = BatchedVoltageControl(net, prof, dict(voltage_barrier_type=cases.SCENARIOS[name]["barrier"]), batch=B, lanes_per_env=G)
         except Exception as e:

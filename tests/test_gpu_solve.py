@@ -30,7 +30,7 @@ def _net(name):
 
 
 @pytest.mark.parametrize("name", ["case33", "case141", "case322", "baran_wu", "rand23"])
-@pytest.mark.parametrize("lanes", [0, 4, 8, 16, 32])
+@pytest.mark.parametrize("lanes", [0, 4, 8, 16, 32, 64, 128])
 def test_solve_matches_golden(name, lanes):
     from mapdn_b200._capi import MapdnError
     g = np.load(os.path.join(GOLD, f"solve_{name}.npz"))
