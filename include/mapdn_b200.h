@@ -139,6 +139,8 @@ typedef struct {
   double tol;                 /* NR tolerance on ||F||inf p.u. [1e-8]; <=0 => default   */
   int32_t max_iter;           /* NR iteration cap [10]; <=0 => default                  */
   int32_t lanes_per_env;      /* 0 = auto; else 4, 8, 16, 32, 64 or 128 threads per env */
+  int32_t state_space_mask;   /* state_space (reference :78): bit0 demand, bit1 pv, bit2 reactive, bit3 vm_pu,
+                                 bit4 va_degree; 0 = all five (the default)              */
 } mapdn_cfg;
 
 typedef struct {

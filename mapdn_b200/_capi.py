@@ -17,6 +17,7 @@ from .network import NetDesc, ProfileDesc
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MAPDN_B200_LIB") or os.path.join(_HERE, "libmapdn_b200.so")   # env override: kernel experiments
 
+STATE_SPACE_BITS = {"demand": 1, "pv": 2, "reactive": 4, "vm_pu": 8, "va_degree": 16}
 BARRIERS = {"l1": 0, "l2": 1, "bowl": 2, "bump": 3, "courant_beltrami": 4}
 INFO_KEYS = ("percentage_of_v_out_of_control", "percentage_of_lower_than_lower_v",
              "percentage_of_higher_than_upper_v", "totally_controllable_ratio",
@@ -53,7 +54,7 @@ class CfgC(C.Structure):
                 ("v_upper", C.c_double), ("v_lower", C.c_double), ("episode_limit", C.c_int32),
                 ("action_low", C.c_double), ("action_high", C.c_double), ("reset_action", C.c_int32),
                 ("seed", C.c_uint64), ("env_id_offset", C.c_int64), ("tol", C.c_double),
-                ("max_iter", C.c_int32), ("lanes_per_env", C.c_int32)]
+                ("max_iter", C.c_int32), ("lanes_per_env", C.c_int32), ("state_space_mask", C.c_int32)]
 
 
 class DimsC(C.Structure):

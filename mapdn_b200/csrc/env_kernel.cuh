@@ -928,16 +928,18 @@ __global__ void __launch_bounds__(G > 32 ? 544 : 160) env_kernel(const __grid_co
       for (int idx = gl; idx < tot; idx += G) o[idx] = s.base[h.obs_off[idx]];
     }
     if (MODE == MODE_RESET && p.state != nullptr) {
-      // get_state (:213-230): [P_bus | Q_bus | pv | q | vm | va(deg)]
+      // get_state (:213-230): [P_bus | Q_bus | pv | q | vm | va(deg)] restricted to state_space (cold program)
       double* o = p.state + static_cast<size_t>(env) * p.state_dim;
       for (int idx = gl; idx < p.state_dim; idx += G) {
-        double v;
-        if (idx < n) v = s.node(h.node_of_bus[idx])[A_BP].x;
-        else if (idx < 2 * n) v = s.node(h.node_of_bus[idx - n])[A_BP].y;
-        else if (idx < 2 * n + ng) v = s.pv[idx - 2 * n];
-        else if (idx < 2 * n + 2 * ng) v = s.q[idx - 2 * n - ng];
-        else if (idx < 3 * n + 2 * ng) v = s.node(h.node_of_bus[idx - 2 * n - 2 * ng])[A_VV].x;
-        else v = s.node(h.node_of_bus[idx - 3 * n - 2 * ng])[A_VV].y * kRad2Deg;
+        const unsigned src = __ldg(p.state_src + idx);
+        const int kind = static_cast<int>(src >> 28), ix = static_cast<int>(src & 0x0FFFFFFFu);
+        double v = 0.0;
+        if (kind == OBS_PBUS) v = s.node(h.node_of_bus[ix])[A_BP].x;
+        else if (kind == OBS_QBUS) v = s.node(h.node_of_bus[ix])[A_BP].y;
+        else if (kind == OBS_PV) v = s.pv[ix];
+        else if (kind == OBS_QSG) v = s.q[ix];
+        else if (kind == OBS_VM) v = s.node(h.node_of_bus[ix])[A_VV].x;
+        else if (kind == OBS_VA_DEG) v = s.node(h.node_of_bus[ix])[A_VV].y * kRad2Deg;
         if (valid) o[idx] = v;
       }
     }

@@ -70,6 +70,7 @@ struct Params {
   const double* lscale; const double* sscale;                 // scaling by load id / sgen id
   const int* sl_node; const double* sl_y;                     // slack-adjacent nodes, Y[slack,i] (G,B)
   const unsigned* obs_src; const int* obs_xptr; const int* obs_xidx;   // cold obs program of get_obs_kernel
+  const unsigned* state_src;                                  // state program: kind | bus / sgen index
   const double* s_max; const double* pv_std; const double* lp_std; const double* lq_std;
   // ---- profile store ----
   const double* prof_pv; const double* prof_lp; const double* prof_lq;
@@ -97,6 +98,7 @@ struct Params {
 };
 
 // cold obs program entry: kind in the top 4 bits, node / sgen index in the low 28
-enum ObsKind { OBS_ZERO = 0, OBS_P = 1, OBS_Q = 2, OBS_PV = 3, OBS_QSG = 4, OBS_VM = 5, OBS_VA = 6 };
+enum ObsKind { OBS_ZERO = 0, OBS_P = 1, OBS_Q = 2, OBS_PV = 3, OBS_QSG = 4, OBS_VM = 5, OBS_VA = 6,
+               OBS_PBUS = 7, OBS_QBUS = 8, OBS_VA_DEG = 9 };   // the last three: get_state (bus index, no add-back)
 
 }  // namespace mapdn

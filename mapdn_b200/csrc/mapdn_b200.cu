@@ -113,20 +113,21 @@ __global__ void get_obs_kernel(const __grid_constant__ Params p) {
   p.obs[gid] = v;
 }
 
-// get_state() (reference :213-230): [P_bus | Q_bus | pv | q | vm | va(deg)]
+// get_state() (reference :213-230): [P_bus | Q_bus | pv | q | vm | va(deg)] restricted to state_space
 __global__ void get_state_kernel(const __grid_constant__ Params p) {
   const long long gid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (gid >= static_cast<long long>(p.nb) * p.state_dim) return;
   const int env = static_cast<int>(gid / p.state_dim), idx = static_cast<int>(gid - static_cast<long long>(env) * p.state_dim);
-  const int n = p.n_bus, ng = p.n_sgen;
-  const size_t eN = static_cast<size_t>(env) * n, eG = static_cast<size_t>(env) * ng;
-  double v;
-  if (idx < n) v = p.res_p[eN + idx];
-  else if (idx < 2 * n) v = p.res_q[eN + idx - n];
-  else if (idx < 2 * n + ng) v = p.cur_pv[eG + idx - 2 * n];
-  else if (idx < 2 * n + 2 * ng) v = p.cur_q[eG + idx - 2 * n - ng];
-  else if (idx < 3 * n + 2 * ng) v = p.res_vm[eN + idx - 2 * n - 2 * ng];
-  else v = p.res_va[eN + idx - 3 * n - 2 * ng] * 57.295779513082320876798;
+  const size_t eN = static_cast<size_t>(env) * p.n_bus, eG = static_cast<size_t>(env) * p.n_sgen;
+  const unsigned src = __ldg(p.state_src + idx);
+  const int kind = static_cast<int>(src >> 28), ix = static_cast<int>(src & 0x0FFFFFFFu);
+  double v = 0.0;
+  if (kind == OBS_PBUS) v = p.res_p[eN + ix];
+  else if (kind == OBS_QBUS) v = p.res_q[eN + ix];
+  else if (kind == OBS_PV) v = p.cur_pv[eG + ix];
+  else if (kind == OBS_QSG) v = p.cur_q[eG + ix];
+  else if (kind == OBS_VM) v = p.res_vm[eN + ix];
+  else if (kind == OBS_VA_DEG) v = p.res_va[eN + ix] * 57.295779513082320876798;
   p.state[gid] = v;
 }
 
@@ -551,41 +552,63 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   }
   // obs program (reference get_obs :232-274): per agent [P_zone | Q_zone | pv | q | vm_zone | va_zone | 0...].
   // Hot copy: double offset of the source inside the env slab. Cold copy (get_obs_kernel): kind | node.
+  const int ssm = (cfg->state_space_mask & 31) ? (cfg->state_space_mask & 31) : 31;
+  const bool ss_dem = ssm & 1, ss_pv = ssm & 2, ss_q = ssm & 4, ss_vm = ssm & 8, ss_va = ssm & 16;
   int obs_dim = 0;
   std::vector<std::vector<int>> zb(ng);
   for (int a = 0; a < ng; ++a) {
     for (int b = 0; b < n; ++b) if (net->bus_zone[b] == net->sgen_zone[a]) zb[a].push_back(b);
-    obs_dim = std::max(obs_dim, 4 * static_cast<int>(zb[a].size()) + 2);
+    const int nz = static_cast<int>(zb[a].size());
+    obs_dim = std::max(obs_dim, nz * (2 * ss_dem + ss_vm + ss_va) + ss_pv + ss_q);
   }
   const int pvq_off2 = kNodeArrays2 * na, scratch_off2 = pvq_off2 + ng;
   if (2 * (scratch_off2 + (ng + 2 * nl + 1) / 2) >= 65535)
     return bail(fail(MAPDN_ERR_UNSUPPORTED, "network too large for 16-bit slab offsets"));
+  // (pvq_off2 is needed by the program; it is defined just above)
   std::vector<uint16_t> obs_off(static_cast<size_t>(ng) * obs_dim);
   std::vector<unsigned> obs_src(static_cast<size_t>(ng) * obs_dim, 0u);
   std::vector<int> obs_xptr(static_cast<size_t>(ng) * obs_dim + 1, 0), obs_xidx;
   enum { K_ZERO = 0, K_P = 1, K_Q = 2, K_PV = 3, K_QSG = 4, K_VM = 5, K_VA = 6 };
   for (int a = 0; a < ng; ++a) {
     const int nz = static_cast<int>(zb[a].size());
+    // entry list of this agent in the reference's order (:254-266), then zero padding (:270-274)
+    std::vector<std::pair<unsigned, int>> ent;           // (kind, bus or sgen)
+    if (ss_dem) { for (int b : zb[a]) ent.push_back({K_P, b}); for (int b : zb[a]) ent.push_back({K_Q, b}); }
+    if (ss_pv) ent.push_back({K_PV, a});
+    if (ss_q) ent.push_back({K_QSG, a});
+    if (ss_vm) for (int b : zb[a]) ent.push_back({K_VM, b});
+    if (ss_va) for (int b : zb[a]) ent.push_back({K_VA, b});
+    (void)nz;
     for (int k = 0; k < obs_dim; ++k) {
       const size_t idx = static_cast<size_t>(a) * obs_dim + k;
       obs_xptr[idx] = static_cast<int>(obs_xidx.size());
       unsigned kind = K_ZERO, ix = 0;
       int off = 2 * (npq * kNodeArrays2 + A_UP);               // sentinel record's UP.x: constant zero
-      if (k < 2 * nz) {
-        const int b = zb[a][k % nz];
-        kind = (k < nz) ? K_P : K_Q; ix = static_cast<unsigned>(node_of_bus[b]);
-        off = 2 * (node_of_bus[b] * kNodeArrays2 + A_OP) + (k < nz ? 0 : 1);
-        for (int j = 0; j < ng; ++j)
-          if (net->sgen_zone[j] == net->sgen_zone[a] && net->sgen_bus[j] == b) obs_xidx.push_back(j);
-      } else if (k == 2 * nz) { kind = K_PV; ix = static_cast<unsigned>(a); off = 2 * pvq_off2 + a; }
-      else if (k == 2 * nz + 1) { kind = K_QSG; ix = static_cast<unsigned>(a); off = 2 * pvq_off2 + ng + a; }
-      else if (k < 3 * nz + 2) { const int i = node_of_bus[zb[a][k - 2 * nz - 2]]; kind = K_VM; ix = i; off = 2 * (i * kNodeArrays2 + A_VV); }
-      else if (k < 4 * nz + 2) { const int i = node_of_bus[zb[a][k - 3 * nz - 2]]; kind = K_VA; ix = i; off = 2 * (i * kNodeArrays2 + A_VV) + 1; }
+      if (k < static_cast<int>(ent.size())) {
+        kind = ent[k].first;
+        const int t2 = ent[k].second;
+        if (kind == K_P || kind == K_Q) {
+          ix = static_cast<unsigned>(node_of_bus[t2]);
+          off = 2 * (node_of_bus[t2] * kNodeArrays2 + A_OP) + (kind == K_P ? 0 : 1);
+          for (int j = 0; j < ng; ++j)
+            if (net->sgen_zone[j] == net->sgen_zone[a] && net->sgen_bus[j] == t2) obs_xidx.push_back(j);
+        } else if (kind == K_PV) { ix = t2; off = 2 * pvq_off2 + t2; }
+        else if (kind == K_QSG) { ix = t2; off = 2 * pvq_off2 + ng + t2; }
+        else { ix = static_cast<unsigned>(node_of_bus[t2]); off = 2 * (node_of_bus[t2] * kNodeArrays2 + A_VV) + (kind == K_VM ? 0 : 1); }
+      }
       obs_src[idx] = (kind << 28) | ix;
       obs_off[idx] = static_cast<uint16_t>(off);
     }
   }
   obs_xptr[static_cast<size_t>(ng) * obs_dim] = static_cast<int>(obs_xidx.size());
+  // state program (reference get_state :213-230), bus-indexed
+  std::vector<unsigned> state_src;
+  if (ss_dem) { for (int b = 0; b < n; ++b) state_src.push_back((7u << 28) | b); for (int b = 0; b < n; ++b) state_src.push_back((8u << 28) | b); }
+  if (ss_pv) for (int j = 0; j < ng; ++j) state_src.push_back((static_cast<unsigned>(K_PV) << 28) | j);
+  if (ss_q) for (int j = 0; j < ng; ++j) state_src.push_back((static_cast<unsigned>(K_QSG) << 28) | j);
+  if (ss_vm) for (int b = 0; b < n; ++b) state_src.push_back((static_cast<unsigned>(K_VM) << 28) | b);
+  if (ss_va) for (int b = 0; b < n; ++b) state_src.push_back((9u << 28) | b);
+  const int state_dim = static_cast<int>(state_src.size());
 
   // ---- 3a. line-loss table + scaling ----
   std::vector<double> lscale = vec_or(net->load_scaling, nl, 1.0), sscale = vec_or(net->sgen_scaling, ng, 1.0);
@@ -714,7 +737,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   // ---- 6. upload + env state ----
   Params& P = e->base;
   P.n_bus = n; P.npq = npq; P.n_load = nl; P.n_sgen = ng; P.n_line = n_line; P.n_lev = n_lev;
-  P.obs_dim = obs_dim; P.state_dim = 4 * n + 2 * ng; P.n_slack_adj = static_cast<int>(sl_node.size());
+  P.obs_dim = obs_dim; P.state_dim = state_dim; P.n_slack_adj = static_cast<int>(sl_node.size());
   P.n_esteps = n_esteps; P.n_bsteps = n_bsteps; P.has_extra_children = max_children > 2;
   P.slack_bus = slack;
   P.nb = cfg->batch; P.env_stride2 = stride2; P.pvq_off2 = pvq_off2; P.scratch_off2 = scratch_off2; P.hot_layout = hl;
@@ -723,7 +746,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   TRY(dev_upload(e, bus_of_node, &P.bus_of_node));
   TRY(dev_upload(e, lscale, &P.lscale)); TRY(dev_upload(e, sscale, &P.sscale));
   TRY(dev_upload(e, sl_node, &P.sl_node)); TRY(dev_upload(e, sl_y, &P.sl_y));
-  TRY(dev_upload(e, obs_src, &P.obs_src)); TRY(dev_upload(e, obs_xptr, &P.obs_xptr)); TRY(dev_upload(e, obs_xidx, &P.obs_xidx));
+  TRY(dev_upload(e, state_src, &P.state_src)); TRY(dev_upload(e, obs_src, &P.obs_src)); TRY(dev_upload(e, obs_xptr, &P.obs_xptr)); TRY(dev_upload(e, obs_xidx, &P.obs_xidx));
   const size_t B = static_cast<size_t>(cfg->batch);
   if (prof) {
     const size_t T = static_cast<size_t>(prof->n_rows);

@@ -68,9 +68,9 @@ class BatchedVoltageControl:
             raise NotImplementedError("only mode='distributed' is supported (decentralised is broken upstream)")
         if args.get("history", 1) != 1:
             raise NotImplementedError("history > 1 is handled by VoltageControl (B=1 shim) only")
-        if list(args["state_space"]) != DEFAULT_ENV_ARGS["state_space"] and \
-                sorted(args["state_space"]) != sorted(DEFAULT_ENV_ARGS["state_space"]):
-            raise NotImplementedError("only the default state_space is supported")
+        unknown = set(args["state_space"]) - set(_capi.STATE_SPACE_BITS)
+        if unknown or not args["state_space"]:
+            raise ValueError(f"state_space must be a non-empty subset of {sorted(_capi.STATE_SPACE_BITS)}, got {unknown}")
         self.args = args
         self.net, self.profiles = net, profiles
         self.batch = int(batch)
@@ -89,7 +89,8 @@ class BatchedVoltageControl:
             action_high=float(args["action_scale"] + args["action_bias"]),
             reset_action=int(bool(args["reset_action"])), seed=int(args["seed"]) & 0xFFFFFFFFFFFFFFFF,
             env_id_offset=int(env_id_offset), tol=float(tol), max_iter=int(max_iter),
-            lanes_per_env=int(lanes_per_env))
+            lanes_per_env=int(lanes_per_env),
+            state_space_mask=sum(_capi.STATE_SPACE_BITS[k] for k in set(args["state_space"])))
         if args["line_weight"] is None and args["q_weight"] is None:
             raise NotImplementedError("Please at least give one weight, either q_weight or line_weight.")
         nd, keep1 = _capi.make_net_desc(net)

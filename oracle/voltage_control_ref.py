@@ -78,7 +78,8 @@ class VoltageControlOracle:
         self.net, self.prof = net, profiles
         self.cfg = dict(voltage_barrier_type="l1", voltage_weight=1.0, q_weight=0.1, line_weight=None,
                         v_upper=1.05, v_lower=0.95, episode_limit=240, history=1, action_scale=0.8,
-                        action_bias=0.0, reset_action=True, seed=0)
+                        action_bias=0.0, reset_action=True, seed=0,
+                        state_space=["pv", "demand", "reactive", "vm_pu", "va_degree"])
         self.cfg.update(cfg)
         c = self.cfg
         self.env_id = env_id
@@ -93,7 +94,9 @@ class VoltageControlOracle:
         self.barrier = VOLTAGE_BARRIER[c["voltage_barrier_type"]]
         self.episode = 0
         self.zones = [net.zone_buses(i) for i in range(net.n_sgen)]
-        self.obs_dim = net.obs_dim
+        ss = self.cfg["state_space"]
+        self.obs_dim = max(len(z) * (2 * ("demand" in ss) + ("vm_pu" in ss) + ("va_degree" in ss)) + ("pv" in ss)
+                           + ("reactive" in ss) for z in self.zones)
 
     # ---- profile access (:440-513) --------------------------------------------------------
     def _row(self, t):
@@ -206,9 +209,20 @@ class VoltageControlOracle:
         return -loss, info
 
     # ---- observations (:213-316, :523-546) --------------------------------------------------
-    def get_state(self):
-        r = self.g.res
-        return np.concatenate([r.p_mw, r.q_mvar, self.g.sgen_p, self.g.sgen_q, r.vm_pu, r.va_degree])
+    def get_state(self):                                              # :213-230
+        r, ss = self.g.res, self.cfg["state_space"]
+        state = []
+        if "demand" in ss:
+            state += list(r.p_mw) + list(r.q_mvar)
+        if "pv" in ss:
+            state += list(self.g.sgen_p)
+        if "reactive" in ss:
+            state += list(self.g.sgen_q)
+        if "vm_pu" in ss:
+            state += list(r.vm_pu)
+        if "va_degree" in ss:
+            state += list(r.va_degree)
+        return np.array(state)
 
     def get_obs(self):
         r, net = self.g.res, self.net
@@ -223,7 +237,17 @@ class VoltageControlOracle:
                     k = np.nonzero(zb == net.sgen_bus[j])[0]
                     p[k] += self.g.sgen_p[j]
                     q[k] += self.g.sgen_q[j]
-            o = np.concatenate([p, q, [self.g.sgen_p[i]], [self.g.sgen_q[i]],
-                                r.vm_pu[zb], r.va_degree[zb] * np.pi / 180])
+            ss, o = self.cfg["state_space"], []                       # :254-266
+            if "demand" in ss:
+                o += list(p) + list(q)
+            if "pv" in ss:
+                o.append(self.g.sgen_p[i])
+            if "reactive" in ss:
+                o.append(self.g.sgen_q[i])
+            if "vm_pu" in ss:
+                o += list(r.vm_pu[zb])
+            if "va_degree" in ss:
+                o += list(r.va_degree[zb] * np.pi / 180)
+            o = np.array(o)
             obs.append(np.concatenate([o, np.zeros(self.obs_dim - o.shape[0])]))
         return obs

@@ -284,3 +284,22 @@ def test_meshed_env_trajectory_matches_oracle():
     rng = np.random.default_rng(1)
     for t in range(3):
         _cmp_step(env, oracles, ids, rng.uniform(-0.8, 0.8, (7, 6)))
+
+
+@pytest.mark.parametrize("ss", [["vm_pu"], ["pv", "reactive"], ["demand", "va_degree"], ["vm_pu", "va_degree", "pv"]])
+def test_state_space_subsets(ss):
+    """state_space selects the blocks of obs / state (reference :78, :217-228, :254-266)."""
+    from oracle.voltage_control_ref import VoltageControlOracle
+    net, prof = cases.make_case("case33"), cases.make_profiles("case33", n_days=4)
+    env = _make(net, prof, dict(state_space=ss, seed=2), batch=5)
+    nz = 12
+    assert env.obs_size == nz * (2 * ("demand" in ss) + ("vm_pu" in ss) + ("va_degree" in ss)) + ("pv" in ss) + ("reactive" in ss)
+    assert env.state_size == 33 * (2 * ("demand" in ss) + ("vm_pu" in ss) + ("va_degree" in ss)) + 6 * (("pv" in ss) + ("reactive" in ss))
+    oracles = [VoltageControlOracle(net, prof, env.args, env_id=i) for i in range(5)]
+    obs, state = env.reset()
+    for o, i in zip(oracles, range(5)):
+        oo, os_ = o.reset()
+        assert np.abs(np.array(oo) - obs[i].cpu().numpy()).max() < TOL and np.abs(os_ - state[i].cpu().numpy()).max() < 1e-8
+    rng = np.random.default_rng(0)
+    for t in range(2):
+        _cmp_step(env, oracles, range(5), rng.uniform(-0.8, 0.8, (5, 6)))
