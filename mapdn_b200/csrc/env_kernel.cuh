@@ -2,7 +2,8 @@
 // Newton-Raphson on the (radial) Ybus with a zero-fill 2x2-block elimination -> reward / info ->
 // next profile row (+ noise) -> zone-masked observation gather. One launch per env step.
 //
-// Work decomposition: G lanes of a warp own one env instance (32/G envs per warp); the env's
+// Work decomposition: a group of G threads owns one env instance - a sub-warp slice (G <= 32: 32/G envs
+// per warp in lock-step) or 2-4 whole warps (G = 64 / 128, large feeders); the env's
 // Newton state lives in shared memory (one 144 B record per PQ bus, 128-bit accesses); the network's
 // admittances, the elimination schedule, the element->bus maps and the observation program
 // (identical for all envs) are staged once per CTA with a TMA bulk copy. The Newton loop never
@@ -25,6 +26,8 @@
 
 namespace mapdn {
 
+// Profile builds (MAPDN_PROFILE_BUILD=1 python -m mapdn_b200.build): clock64 totals per phase of warp 0 of block 0,
+// printed by launch_env_kernel (scripts/phase_prof.py). Compiled out otherwise.
 #ifdef MAPDN_PROFILE
 #define PROF_DECL long long _pt = clock64(); long long _acc[12] = {0,0,0,0,0,0,0,0,0,0,0,0};
 #define PROF(k) { long long _t = clock64(); _acc[k] += _t - _pt; _pt = _t; }
@@ -229,7 +232,7 @@ struct Hot {
   const double2* nbr_y;
 };
 struct Slab {
-  double2* nodes;   // (npq + 1) records of kNodeArrays2 double2
+  double2* nodes;   // (npq + 2) records of kNodeArrays2 double2 (sentinel + trash at the end)
   double* base;     // the slab as a flat double array (obs program offsets index this)
   double* pv;       // sgen.p_mw   [n_sgen]
   double* q;        // sgen.q_mvar [n_sgen]

@@ -564,13 +564,11 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   const int pvq_off2 = kNodeArrays2 * na, scratch_off2 = pvq_off2 + ng;
   if (2 * (scratch_off2 + (ng + 2 * nl + 1) / 2) >= 65535)
     return bail(fail(MAPDN_ERR_UNSUPPORTED, "network too large for 16-bit slab offsets"));
-  // (pvq_off2 is needed by the program; it is defined just above)
   std::vector<uint16_t> obs_off(static_cast<size_t>(ng) * obs_dim);
   std::vector<unsigned> obs_src(static_cast<size_t>(ng) * obs_dim, 0u);
   std::vector<int> obs_xptr(static_cast<size_t>(ng) * obs_dim + 1, 0), obs_xidx;
   enum { K_ZERO = 0, K_P = 1, K_Q = 2, K_PV = 3, K_QSG = 4, K_VM = 5, K_VA = 6 };
   for (int a = 0; a < ng; ++a) {
-    const int nz = static_cast<int>(zb[a].size());
     // entry list of this agent in the reference's order (:254-266), then zero padding (:270-274)
     std::vector<std::pair<unsigned, int>> ent;           // (kind, bus or sgen)
     if (ss_dem) { for (int b : zb[a]) ent.push_back({K_P, b}); for (int b : zb[a]) ent.push_back({K_Q, b}); }
@@ -578,7 +576,6 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     if (ss_q) ent.push_back({K_QSG, a});
     if (ss_vm) for (int b : zb[a]) ent.push_back({K_VM, b});
     if (ss_va) for (int b : zb[a]) ent.push_back({K_VA, b});
-    (void)nz;
     for (int k = 0; k < obs_dim; ++k) {
       const size_t idx = static_cast<size_t>(a) * obs_dim + k;
       obs_xptr[idx] = static_cast<int>(obs_xidx.size());
