@@ -711,9 +711,11 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   // put 1..4 envs of G threads in a CTA. Fewer envs per CTA when that spreads the batch over all SMs.
   auto smem_for = [&](int epb) { return static_cast<size_t>(hl.bytes) + static_cast<size_t>(epb) * stride2 * 16; };
   const int unit = (G <= 32) ? 32 / G : 1;               // envs added per step of the search
-  int epb = 4 * unit;
+  // measured on B200 (profiles/): two solver warps per CTA for small sub-warp groups, four for one-warp envs,
+  // as many multi-warp envs as fit (<= 512 solver threads)
+  int epb = (G <= 16) ? 2 * unit : 4 * unit;
   if (G > 32) while (epb > 1 && epb * G > 512) --epb;
-  while (epb > unit && (cfg->batch + epb - 1) / epb < 2 * dp.multiProcessorCount) epb = (G <= 32) ? epb / 2 : epb - 1;
+  if (const char* ov = getenv("MAPDN_EPB")) epb = std::max(unit, atoi(ov) / unit * unit);   // tuning override
   while (epb > unit && smem_for(epb) > max_smem) epb -= unit;
   if (smem_for(epb) > max_smem)
     return bail(fail(MAPDN_ERR_UNSUPPORTED, "network too large for the shared-memory resident solver (" +
