@@ -383,7 +383,7 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
         s01 = make_double2(sa00 * idet, sa01 * idet);
         s23 = make_double2(sa10 * idet, sa11 * idet);
         tt = make_double2(ta0 * idet, ta1 * idet);
-        nd[A_UP] = s01; nd[A_DN] = s23; nd[A_T] = tt;
+        if (fl & kEschedStore) { nd[A_UP] = s01; nd[A_DN] = s23; nd[A_T] = tt; }   // else: it travels in registers
         nd[A_R] = make_double2(c0v, c1v);                         // D^-1 r  (becomes dx in the back sweep)
         nd[A_D01] = make_double2(m00, m01);                       // D^-1 J[i,p]
         nd[A_D23] = make_double2(m10, m11);

@@ -30,6 +30,7 @@ constexpr uint32_t kNone = 0xFFFFu;   // "no parent" in 16-bit node fields
 constexpr unsigned kEschedReg0 = 0x100u;    // registers of the same lane (it eliminated child 0 in the previous step)
 constexpr unsigned kEschedLoad0 = 0x200u;   // shared memory
 constexpr unsigned kEschedLoad1 = 0x400u;   // child 1 exists (always from shared memory)
+constexpr unsigned kEschedStore = 0x800u;   // the parent will read this bus's Schur update from shared memory
 
 struct HotLayout {        // byte offsets inside the hot static blob (staged into smem per CTA)
   int yup, ydn;           // double2 [npq]: Y[i,parent], Y[parent,i]   (G, B)

@@ -455,7 +455,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   const int trash = npq + 1;
   std::vector<uint64_t> esched, bsched;
   {
-    std::vector<int> lane_of(npq, -1), step_of(npq, -1);
+    std::vector<int> lane_of(npq, -1), step_of(npq, -1), reg_child(npq, -1), epos(npq, -1);
     int cur = 0;
     for (int l = 0; l < n_lev; ++l) {
       const int w = elev[l + 1] - elev[l], nst = (w + G - 1) / G;
@@ -484,12 +484,17 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
         } else if (nchild[i] >= 1) {
           const int a0 = inh[i] >= 0 ? inh[i] : cfirst[i];
           c0 = a0; fl = (inh[i] >= 0 && sidx / G == 0) ? kEschedReg0 : kEschedLoad0;
+          if (fl & kEschedReg0) reg_child[i] = a0;
           if (nchild[i] == 2) { c1 = (a0 == cfirst[i]) ? cfirst[i] + 1 : cfirst[i]; fl |= kEschedLoad1; }
         }
+        epos[i] = static_cast<int>(esched.size());
         esched.push_back(static_cast<uint64_t>(i) | (c0 << 16) | (c1 << 32) | (fl << 48));
       }
       cur += nst;
     }
+    // a bus stores its Schur update only if its parent will fetch it from shared memory
+    for (int i = 0; i < npq; ++i)
+      if (parent[i] >= 0 && reg_child[parent[i]] != i) esched[epos[i]] |= static_cast<uint64_t>(kEschedStore) << 48;
     // back sweep by depth: children inherit the lane of their parent (the child with the tallest subtree first)
     std::fill(lane_of.begin(), lane_of.end(), -1); std::fill(step_of.begin(), step_of.end(), -1);
     cur = 0;
