@@ -276,7 +276,7 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
   while (true) {
     PROF(2)
     // --- per-edge terms of (i, parent): row i / col parent and row parent / col i ---
-#pragma unroll 2
+#pragma unroll 4
     for (int i = gl; i < npq; i += G) {
       const int pa = static_cast<int>(static_cast<uint32_t>(h.ndesc[i]) & 0xFFFFu);   // roots: sentinel, Y = 0
       double2* nd = s.node(i);
@@ -291,7 +291,7 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
     PROF(3)
     // --- mismatch F = S_calc - S_spec and diagonal Jacobian blocks ---
     double nrm = 0.0;
-#pragma unroll 2
+#pragma unroll 4
     for (int i = gl; i < npq; i += G) {
       const uint64_t ndc = h.ndesc[i];
       const int c0 = static_cast<int>((ndc >> 16) & 0xFFFFu), c1 = static_cast<int>((ndc >> 32) & 0xFFFFu);
@@ -422,7 +422,7 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
     }
     PROF(6)
     // --- update (theta += dtheta, V += V * dV/V) and V = Vm exp(j theta) ---
-#pragma unroll 2
+#pragma unroll 4
     for (int i = gl; i < npq; i += G) {
       if (!done) {
         double2* nd = s.node(i);
@@ -688,7 +688,7 @@ __global__ void __launch_bounds__(G > 32 ? 544 : 160) env_kernel(const __grid_co
       if (MODE == MODE_RESET) { row = start + 1; if (row > p.n_rows - 1) row = p.n_rows - 1; }   // t = steps = 1
       const uint32_t c1 = kResetFlag | static_cast<uint32_t>(attempt);
       // (1) coalesced, independent loads of the env's element values into shared memory
-#pragma unroll 2
+#pragma unroll 4
       for (int j = gl; j < ng; j += G) {
         double pv, q;
         if (MODE == MODE_SOLVE) {
@@ -830,7 +830,7 @@ __global__ void __launch_bounds__(G > 32 ? 544 : 160) env_kernel(const __grid_co
     // per-bus results + voltage statistics (reference _calc_reward :584-596, :610)
     double cnt_lo = 0, cnt_hi = 0, sum_dev = 0, sum_v = 0, max_drop = 0, max_rise = 0, sum_bar = 0;
     const double v_ref = 0.5 * (p.v_lower + p.v_upper);
-#pragma unroll 2
+#pragma unroll 4
     for (int b = gl; b < n; b += G) {
       const double2* nd = s.node(h.node_of_bus[b]);
       const double2 vv = nd[A_VV], bp = nd[A_BP];
@@ -861,7 +861,7 @@ __global__ void __launch_bounds__(G > 32 ? 544 : 160) env_kernel(const __grid_co
     double sum_pl = 0.0;
     {
       const size_t ePL = static_cast<size_t>(env) * p.n_line;
-#pragma unroll 2
+#pragma unroll 4
       for (int k = gl; k < p.n_line; k += G) {
         const double2 vf = s.node(h.line_nodes[2 * k])[A_EF], vt = s.node(h.line_nodes[2 * k + 1])[A_EF];
         const double cc = vf.x * vt.x + vf.y * vt.y, ss = vf.y * vt.x - vf.x * vt.y;

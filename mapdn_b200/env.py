@@ -117,6 +117,11 @@ class BatchedVoltageControl:
             self.terminated = torch.zeros(B, dtype=torch.uint8, device=self.device)
             self.info = torch.zeros(B, len(INFO_KEYS), dtype=f64, device=self.device)
         self._host = None
+        # raw pointers of the internal buffers (ctypes converts plain ints for c_void_p parameters): keeps the
+        # per-step Python overhead of the hot call small
+        self._p_obs, self._p_state = self.obs.data_ptr(), self.state.data_ptr()
+        self._p_reward, self._p_term, self._p_info = self.reward.data_ptr(), self.terminated.data_ptr(), self.info.data_ptr()
+        self._act_shape = (self.batch, self.n_agents)
 
     # ------------------------------------------------------------------------------------------
     def close(self):
@@ -162,10 +167,14 @@ class BatchedVoltageControl:
     def step(self, actions: torch.Tensor, add_noise: bool = True, want_obs: bool = True, want_info: bool = True):
         """One transition of every env. Returns (reward ``[B]``, terminated ``[B]`` uint8,
         info ``[B,11]`` in INFO_KEYS order); the new observations are in ``self.obs``."""
-        self._chk(actions, (self.batch, self.n_agents), name="actions")
-        _capi.check(self._L.mapdn_step(self._h, _ptr(actions), int(add_noise), _ptr(self.reward),
-                                       _ptr(self.terminated), _ptr(self.info) if want_info else None,
-                                       _ptr(self.obs) if want_obs else None, self._stream()))
+        if (actions.dtype is not torch.float64 or tuple(actions.shape) != self._act_shape or actions.device != self.device
+                or not actions.is_contiguous()):
+            self._chk(actions, self._act_shape, name="actions")
+        st = self._L.mapdn_step(self._h, actions.data_ptr(), int(add_noise), self._p_reward, self._p_term,
+                                self._p_info if want_info else None, self._p_obs if want_obs else None,
+                                torch.cuda.current_stream(self.device).cuda_stream)
+        if st:
+            _capi.check(st)
         return self.reward, self.terminated, self.info
 
     # host-buffer path (what a CPU-side caller such as the reference trainer pays end to end)
