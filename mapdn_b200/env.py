@@ -66,8 +66,7 @@ class BatchedVoltageControl:
             # the reference's decentralised mode raises KeyError in get_obs at this commit
             # (voltage_control_env.py:239 indexes clusters["sgen{i}"], absent in that mode)
             raise NotImplementedError("only mode='distributed' is supported (decentralised is broken upstream)")
-        if args.get("history", 1) != 1:
-            raise NotImplementedError("history > 1 is handled by VoltageControl (B=1 shim) only")
+        self.history = int(args.get("history", 1) or 1)
         unknown = set(args["state_space"]) - set(_capi.STATE_SPACE_BITS)
         if unknown or not args["state_space"]:
             raise ValueError(f"state_space must be a non-empty subset of {sorted(_capi.STATE_SPACE_BITS)}, got {unknown}")
@@ -116,6 +115,7 @@ class BatchedVoltageControl:
             self.reward = torch.zeros(B, dtype=f64, device=self.device)
             self.terminated = torch.zeros(B, dtype=torch.uint8, device=self.device)
             self.info = torch.zeros(B, len(INFO_KEYS), dtype=f64, device=self.device)
+        self._hist = None       # [B, history, n_agents, obs_dim] ring of the last observations (history > 1)
         self._host = None
         # raw pointers of the internal buffers (ctypes converts plain ints for c_void_p parameters): keeps the
         # per-step Python overhead of the hot call small
@@ -162,6 +162,13 @@ class BatchedVoltageControl:
                                         _ptr(self.state), self._stream()))
         if mask is not None:   # state of the untouched envs
             _capi.check(self._L.mapdn_get_state(self._h, _ptr(self.state), self._stream()))
+        if self.history > 1:
+            if self._hist is None or mask is None:
+                self._hist = torch.zeros(self.batch, self.history, self.n_agents, self.obs_size, dtype=torch.float64,
+                                         device=self.device)
+            else:
+                self._hist[mask.bool()] = 0.0
+            self._hist[:, -1] = self.obs
         return self.obs, self.state
 
     def step(self, actions: torch.Tensor, add_noise: bool = True, want_obs: bool = True, want_info: bool = True):
@@ -175,6 +182,9 @@ class BatchedVoltageControl:
                                 torch.cuda.current_stream(self.device).cuda_stream)
         if st:
             _capi.check(st)
+        if self.history > 1 and want_obs and self._hist is not None:
+            self._hist = torch.roll(self._hist, -1, dims=1)
+            self._hist[:, -1] = self.obs
         return self.reward, self.terminated, self.info
 
     # host-buffer path (what a CPU-side caller such as the reference trainer pays end to end)
@@ -199,6 +209,13 @@ class BatchedVoltageControl:
             C.c_void_p(hb["terminated"].data_ptr()), C.c_void_p(hb["info"].data_ptr()),
             C.c_void_p(hb["obs"].data_ptr()), self._stream()))
         return hb["reward"].numpy(), hb["terminated"].numpy(), hb["info"].numpy(), hb["obs"].numpy()
+
+    def get_obs_stacked(self) -> torch.Tensor:
+        """``history`` stacked observations ``[B, n_agents, history * obs_dim]``, oldest frame first and zero frames
+        before the episode start (reference :303-315; one frame per reset / step, not per ``get_obs`` call)."""
+        if self.history <= 1 or self._hist is None:
+            return self.obs
+        return self._hist.permute(0, 2, 1, 3).reshape(self.batch, self.n_agents, self.history * self.obs_size)
 
     # ---- getters ------------------------------------------------------------------------------
     def get_obs(self) -> torch.Tensor:

@@ -303,3 +303,22 @@ def test_state_space_subsets(ss):
     rng = np.random.default_rng(0)
     for t in range(2):
         _cmp_step(env, oracles, range(5), rng.uniform(-0.8, 0.8, (5, 6)))
+
+
+def test_batched_history_stacking():
+    net, prof = cases.make_case("case33"), cases.make_profiles("case33", n_days=4)
+    env = _make(net, prof, dict(history=3, seed=1, episode_limit=4), batch=6)
+    env.reset()
+    o0 = env.obs.clone()
+    st = env.get_obs_stacked()
+    assert st.shape == (6, 6, 150) and torch.equal(st[:, :, 100:], o0) and float(st[:, :, :100].abs().max()) == 0.0
+    a = torch.zeros(6, 6, dtype=torch.float64, device=env.device)
+    env.step(a); o1 = env.obs.clone()
+    st = env.get_obs_stacked()
+    assert torch.equal(st[:, :, 50:100], o0) and torch.equal(st[:, :, 100:], o1)
+    env.step(a); _, done, _ = env.step(a)
+    assert bool(done.all())
+    mask = torch.tensor([1, 0, 0, 1, 0, 0], dtype=torch.uint8, device=env.device)
+    env.reset(mask=mask)
+    st = env.get_obs_stacked()
+    assert float(st[0, :, :100].abs().max()) == 0.0 and float(st[1, :, :100].abs().max()) > 0.0
