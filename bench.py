@@ -267,6 +267,23 @@ def run_ours(args):
     e2e_val = B * world * Ke / float(te.item())
     h2d = B * env.n_agents * 8
     d2h = B * (8 + 1 + 11 * 8 + env.n_agents * env.obs_size * 8)
+    # variant: observations delivered in fp32 (what the reference's learners consume after prep_obs)
+    env.reset(); state["t"] = 0
+    for i in range(3):
+        env.step_host(host_acts[i % 4], obs_dtype=np.float32)
+    sync_all()
+    e0 = time.perf_counter()
+    for i in range(Ke):
+        if state["t"] == ep_len:
+            env.reset(); state["t"] = 0
+        env.step_host(host_acts[i % 4], obs_dtype=np.float32)
+        state["t"] += 1
+    sync_all()
+    te32 = torch.tensor([time.perf_counter() - e0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te32, op=dist.ReduceOp.MAX)
+    e2e32_val = B * world * Ke / float(te32.item())
+    d2h32 = B * (8 + 1 + 11 * 8 + env.n_agents * env.obs_size * 4)
 
     if rank != 0:
         if world > 1:
@@ -314,7 +331,10 @@ def run_ours(args):
                             l2="flushed between steps (256 MiB memset, outside the event pairs)" if flush is not None
                             else "not flushed", timing="sum of per-step CUDA-event pairs, max over ranks"),
                 clocks=clk, gpu_launches=int(launches),
-                e2e=dict(value=e2e_val, unit="env-steps/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=Ke),
+                e2e=dict(value=e2e_val, unit="env-steps/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=Ke,
+                         obs_dtype="f64"),
+                e2e_obs_f32=dict(value=e2e32_val, unit="env-steps/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h32,
+                                 steps=Ke, note="same call with observations delivered in fp32 (opt-in API)"),
                 roofline=roofline, cpu_baseline=cpu, wall_ms_per_step=(w1 - w0) / K * 1e3)
     print(json.dumps(line), flush=True)
     if world > 1:

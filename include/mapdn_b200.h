@@ -188,6 +188,17 @@ mapdn_status mapdn_step_host(mapdn_env* env, const double* actions_host, int32_t
                              double* reward_host, uint8_t* terminated_host, double* info_host,
                              double* obs_host, void* stream);
 
+/*
+ * Variants that deliver the observations in fp32 - what the reference's learners consume (prep_obs casts to
+ * float32 right away, reference utilities/util.py:137-147). Halves the device->host traffic of the host-buffer
+ * path; everything else (reward, info, the env state itself) stays fp64.
+ */
+mapdn_status mapdn_step_f32obs(mapdn_env* env, const double* actions_dev, int32_t add_noise, double* reward_dev,
+                               uint8_t* terminated_dev, double* info_dev, float* obs_dev, void* stream);
+mapdn_status mapdn_step_host_f32obs(mapdn_env* env, const double* actions_host, int32_t add_noise,
+                                    double* reward_host, uint8_t* terminated_host, double* info_host,
+                                    float* obs_host, void* stream);
+
 mapdn_status mapdn_get_obs(mapdn_env* env, double* obs_dev, void* stream);      /* :232-316 */
 mapdn_status mapdn_get_state(mapdn_env* env, double* state_dev, void* stream);  /* :213-230 */
 mapdn_status mapdn_get_field(mapdn_env* env, int32_t field, double* out_dev, void* stream);

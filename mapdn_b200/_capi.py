@@ -65,7 +65,7 @@ class DimsC(C.Structure):
 
 
 EXPORTS = ("mapdn_abi_version", "mapdn_last_error", "mapdn_create", "mapdn_destroy", "mapdn_get_dims",
-           "mapdn_reset", "mapdn_step", "mapdn_step_host", "mapdn_get_obs", "mapdn_get_state",
+           "mapdn_reset", "mapdn_step", "mapdn_step_host", "mapdn_step_f32obs", "mapdn_step_host_f32obs", "mapdn_get_obs", "mapdn_get_state",
            "mapdn_get_field", "mapdn_solve", "mapdn_get_ybus_dense", "mapdn_launch_count")
 
 _lib: Optional[C.CDLL] = None
@@ -94,6 +94,8 @@ def lib() -> C.CDLL:
     L.mapdn_reset.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp]
     L.mapdn_step.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, vp]
     L.mapdn_step_host.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, vp]
+    L.mapdn_step_f32obs.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, vp]
+    L.mapdn_step_host_f32obs.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, vp]
     L.mapdn_get_obs.argtypes = [vp, vp, vp]
     L.mapdn_get_state.argtypes = [vp, vp, vp]
     L.mapdn_get_field.argtypes = [vp, C.c_int32, vp, vp]

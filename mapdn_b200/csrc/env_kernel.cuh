@@ -929,6 +929,11 @@ __global__ void __launch_bounds__(G > 32 ? 544 : 160) env_kernel(const __grid_co
       const int tot = ng * p.obs_dim;
 #pragma unroll 4
       for (int idx = gl; idx < tot; idx += G) o[idx] = s.base[h.obs_off[idx]];
+    } else if (MODE == MODE_STEP && p.obs32 != nullptr && valid) {
+      float* o = p.obs32 + static_cast<size_t>(env) * ng * p.obs_dim;
+      const int tot = ng * p.obs_dim;
+#pragma unroll 4
+      for (int idx = gl; idx < tot; idx += G) o[idx] = static_cast<float>(s.base[h.obs_off[idx]]);
     }
     if (MODE == MODE_RESET && p.state != nullptr) {
       // get_state (:213-230): [P_bus | Q_bus | pv | q | vm | va(deg)] restricted to state_space (cold program)

@@ -93,6 +93,7 @@ struct Params {
   double* out_vm; double* out_va; double* out_p; double* out_q; double* out_pl;
   int* out_iters; unsigned char* out_conv;
   double* reward; unsigned char* term; double* info; double* obs; double* state;
+  float* obs32;           // alternative fp32 destination of the observations (MODE_STEP)
   double* dense_ws;       // meshed nets only: per resident env group, (2 npq) x (2 npq + 1) doubles [J | rhs]
   int dense_stride;       // doubles per group in dense_ws
   long long* prof;        // MAPDN_PROFILE builds: per-phase clock64 totals of warp 0 of block 0

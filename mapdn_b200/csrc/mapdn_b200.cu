@@ -864,6 +864,36 @@ mapdn_status mapdn_step_host(mapdn_env* e, const double* actions_host, int32_t a
   return MAPDN_OK;
 }
 
+mapdn_status mapdn_step_f32obs(mapdn_env* e, const double* actions_dev, int32_t add_noise, double* reward_dev,
+                               uint8_t* terminated_dev, double* info_dev, float* obs_dev, void* stream) {
+  if (!e || !actions_dev || !reward_dev || !terminated_dev) return fail(MAPDN_ERR_INVALID, "null argument");
+  if (!e->base.prof_pv) return fail(MAPDN_ERR_INVALID, "handle was created without a profile store");
+  MAPDN_CUDA(cudaSetDevice(e->device));
+  Params p = e->base;
+  p.actions = actions_dev; p.add_noise = add_noise; p.reward = reward_dev; p.term = terminated_dev;
+  p.info = info_dev; p.obs = nullptr; p.obs32 = obs_dev;
+  return launch_env_kernel(e, MODE_STEP, p, static_cast<cudaStream_t>(stream));
+}
+
+mapdn_status mapdn_step_host_f32obs(mapdn_env* e, const double* actions_host, int32_t add_noise, double* reward_host,
+                                    uint8_t* terminated_host, double* info_host, float* obs_host, void* stream) {
+  if (!e || !actions_host || !reward_host || !terminated_host) return fail(MAPDN_ERR_INVALID, "null argument");
+  MAPDN_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t B = e->dims.batch, ng = e->dims.n_sgen, od = e->dims.obs_dim;
+  float* d_obs32 = reinterpret_cast<float*>(e->d_stage_obs);          // the fp64 staging buffer is large enough
+  MAPDN_CUDA(cudaMemcpyAsync(e->d_stage_actions, actions_host, B * ng * sizeof(double), cudaMemcpyHostToDevice, st));
+  mapdn_status s = mapdn_step_f32obs(e, e->d_stage_actions, add_noise, e->d_stage_reward, e->d_stage_term,
+                                     info_host ? e->d_stage_info : nullptr, obs_host ? d_obs32 : nullptr, stream);
+  if (s != MAPDN_OK) return s;
+  MAPDN_CUDA(cudaMemcpyAsync(reward_host, e->d_stage_reward, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  MAPDN_CUDA(cudaMemcpyAsync(terminated_host, e->d_stage_term, B, cudaMemcpyDeviceToHost, st));
+  if (info_host) MAPDN_CUDA(cudaMemcpyAsync(info_host, e->d_stage_info, B * MAPDN_N_INFO * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (obs_host) MAPDN_CUDA(cudaMemcpyAsync(obs_host, d_obs32, B * ng * od * sizeof(float), cudaMemcpyDeviceToHost, st));
+  MAPDN_CUDA(cudaStreamSynchronize(st));
+  return MAPDN_OK;
+}
+
 mapdn_status mapdn_get_obs(mapdn_env* e, double* obs_dev, void* stream) {
   if (!e || !obs_dev) return fail(MAPDN_ERR_INVALID, "null argument");
   MAPDN_CUDA(cudaSetDevice(e->device));

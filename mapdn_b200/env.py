@@ -196,19 +196,24 @@ class BatchedVoltageControl:
                 reward=torch.zeros(B, dtype=torch.float64, **pin),
                 terminated=torch.zeros(B, dtype=torch.uint8, **pin),
                 info=torch.zeros(B, len(INFO_KEYS), dtype=torch.float64, **pin),
-                obs=torch.zeros(B, self.n_agents, self.obs_size, dtype=torch.float64, **pin))
+                obs=torch.zeros(B, self.n_agents, self.obs_size, dtype=torch.float64, **pin),
+                obs32=torch.zeros(B, self.n_agents, self.obs_size, dtype=torch.float32, **pin))
         return self._host
 
-    def step_host(self, actions: np.ndarray, add_noise: bool = True):
+    def step_host(self, actions: np.ndarray, add_noise: bool = True, obs_dtype=np.float64):
         """NumPy in / NumPy out: H2D(actions) + fused step + D2H(reward, terminated, info, obs).
-        Returns views of pinned host buffers (overwritten by the next call)."""
+        ``obs_dtype=np.float32`` delivers the observations in fp32 (what the reference's learners use after
+        ``prep_obs``), halving the device->host traffic. Returns views of pinned host buffers (overwritten by the
+        next call)."""
         hb = self._host_buffers()
         hb["actions"].numpy()[...] = actions
-        _capi.check(self._L.mapdn_step_host(
-            self._h, C.c_void_p(hb["actions"].data_ptr()), int(add_noise), C.c_void_p(hb["reward"].data_ptr()),
-            C.c_void_p(hb["terminated"].data_ptr()), C.c_void_p(hb["info"].data_ptr()),
-            C.c_void_p(hb["obs"].data_ptr()), self._stream()))
-        return hb["reward"].numpy(), hb["terminated"].numpy(), hb["info"].numpy(), hb["obs"].numpy()
+        f32 = np.dtype(obs_dtype) == np.float32
+        fn = self._L.mapdn_step_host_f32obs if f32 else self._L.mapdn_step_host
+        obs = hb["obs32"] if f32 else hb["obs"]
+        _capi.check(fn(self._h, hb["actions"].data_ptr(), int(add_noise), hb["reward"].data_ptr(),
+                       hb["terminated"].data_ptr(), hb["info"].data_ptr(), obs.data_ptr(),
+                       torch.cuda.current_stream(self.device).cuda_stream))
+        return hb["reward"].numpy(), hb["terminated"].numpy(), hb["info"].numpy(), obs.numpy()
 
     def get_obs_stacked(self) -> torch.Tensor:
         """``history`` stacked observations ``[B, n_agents, history * obs_dim]``, oldest frame first and zero frames

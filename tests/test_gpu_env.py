@@ -188,6 +188,16 @@ def test_step_host_equals_device_path():
         torch.cuda.synchronize()
         assert np.array_equal(r1.cpu().numpy(), r2) and np.array_equal(t1.cpu().numpy(), t2)
         assert np.array_equal(i1.cpu().numpy(), i2) and np.array_equal(e1.obs.cpu().numpy(), o2)
+    # fp32 observations: the same values rounded once
+    e3 = _make(net, prof, dict(seed=4, voltage_barrier_type="bowl"), batch=32)
+    e3.reset()
+    a = np.random.default_rng(0).uniform(-0.8, 0.8, (32, 6))
+    e1b = _make(net, prof, dict(seed=4, voltage_barrier_type="bowl"), batch=32); e1b.reset()
+    e1b.step(torch.tensor(a, device=e1b.device))
+    r3, t3, i3, o3 = e3.step_host(a, obs_dtype=np.float32)
+    torch.cuda.synchronize()
+    assert o3.dtype == np.float32 and np.array_equal(o3, e1b.obs.cpu().numpy().astype(np.float32))
+    assert np.array_equal(r3, e1b.reward.cpu().numpy())
 
 
 def test_voltage_control_shim_api():
