@@ -384,11 +384,14 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
         s23 = make_double2(sa10 * idet, sa11 * idet);
         tt = make_double2(ta0 * idet, ta1 * idet);
         if (fl & kEschedStore) { nd[A_UP] = s01; nd[A_DN] = s23; nd[A_T] = tt; }   // else: it travels in registers
-        nd[A_R] = make_double2(c0v, c1v);                         // D^-1 r  (becomes dx in the back sweep)
-        nd[A_D01] = make_double2(m00, m01);                       // D^-1 J[i,p]
-        nd[A_D23] = make_double2(m10, m11);
+        if (!(fl & kEschedIdle)) {
+          nd[A_R] = make_double2(c0v, c1v);                       // D^-1 r  (becomes dx in the back sweep)
+          nd[A_D01] = make_double2(m00, m01);                     // D^-1 J[i,p]
+          nd[A_D23] = make_double2(m10, m11);
+        }
         ed = ed_next; ed_next = ed_next2; own = own_next;
       }
+      grp_sync<G>(gidx);                                 // the last step's results are visible to the back sweep
     }
     PROF(5)
     // --- back substitution root -> leaves, same flat-schedule form (roots: dx = D^-1 r already); a lane
@@ -414,7 +417,7 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
         double2 x = own.x;
         x.x -= own.m01.x * xp.x + own.m01.y * xp.y;
         x.y -= own.m23.x * xp.x + own.m23.y * xp.y;
-        nd[A_R] = x;
+        if (!((bd >> 33) & 1u)) nd[A_R] = x;             // idle lanes (trash record) store nothing
         xl = x;
         bd = bd_next; bd_next = bd_next2; own = own_next;
       }

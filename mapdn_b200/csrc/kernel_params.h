@@ -30,6 +30,7 @@ constexpr uint32_t kNone = 0xFFFFu;   // "no parent" in 16-bit node fields
 constexpr unsigned kEschedReg0 = 0x100u;    // registers of the same lane (it eliminated child 0 in the previous step)
 constexpr unsigned kEschedLoad0 = 0x200u;   // shared memory
 constexpr unsigned kEschedLoad1 = 0x400u;   // child 1 exists (always from shared memory)
+constexpr unsigned kEschedIdle = 0x1000u;   // idle lane of this step: reads the trash record, stores nothing
 constexpr unsigned kEschedStore = 0x800u;   // the parent will read this bus's Schur update from shared memory
 
 struct HotLayout {        // byte offsets inside the hot static blob (staged into smem per CTA)
@@ -38,7 +39,7 @@ struct HotLayout {        // byte offsets inside the hot static blob (staged int
   int ndesc;              // uint64 [npq]: node descriptor, see below
   int esched;             // uint64 [n_esteps * G]: elimination schedule, one entry per (step, lane):
                           //   node | child0<<16 | child1<<32 | flags<<48   (idle lane: trash record)
-  int bsched;             // uint64 [n_bsteps * G]: back-substitution schedule: node | parent<<16 | reg_parent<<32
+  int bsched;             // uint64 [n_bsteps * G]: back-substitution schedule: node | parent<<16 | reg_parent<<32 | idle<<33
   int lptr, lidx;         // uint16 [npq+2], [n_load]: node -> loads (CSR); node npq = slack bus
   int sptr, sidx;         // uint16 [npq+2], [n_sgen]: node -> sgens
   int xptr, xidx;         // uint16 [npq+2], [<=n_sgen]: node -> sgens of the node's own zone (obs add-back)

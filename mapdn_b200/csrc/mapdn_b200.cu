@@ -475,7 +475,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
       for (int sidx = 0; sidx < nst * G; ++sidx) {
         const int i = slot[sidx];
         if (i < 0) { esched.push_back(static_cast<uint64_t>(trash) | (static_cast<uint64_t>(npq) << 16) |
-                                      (static_cast<uint64_t>(npq) << 32) | (static_cast<uint64_t>(kEschedReg0) << 48)); continue; }
+                                      (static_cast<uint64_t>(npq) << 32) | (static_cast<uint64_t>(kEschedReg0 | kEschedIdle) << 48)); continue; }
         lane_of[i] = sidx % G; step_of[i] = cur + sidx / G;
         uint64_t c0 = npq, c1 = npq, fl = 0;
         if (nchild[i] > 2) {
@@ -515,7 +515,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
       for (int i : rest) { while (slot[pos] >= 0) ++pos; slot[pos] = i; }
       for (int sidx = 0; sidx < nst * G; ++sidx) {
         const int i = slot[sidx];
-        if (i < 0) { bsched.push_back(static_cast<uint64_t>(trash) | (static_cast<uint64_t>(npq) << 16) | (1ull << 32)); continue; }
+        if (i < 0) { bsched.push_back(static_cast<uint64_t>(trash) | (static_cast<uint64_t>(npq) << 16) | (3ull << 32)); continue; }
         lane_of[i] = sidx % G; step_of[i] = cur + sidx / G;
         bsched.push_back(static_cast<uint64_t>(i) | (static_cast<uint64_t>(parent[i]) << 16) |
                          (static_cast<uint64_t>(reg[i] && sidx / G == 0) << 32));
@@ -532,7 +532,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
             esched.size() / G, nreal, nreg, nl0, nl1, bsched.size() / G, breal, breg);
   }
   const int n_esteps = static_cast<int>(esched.size()) / G, n_bsteps = static_cast<int>(bsched.size()) / G;
-  if (bsched.empty()) bsched.assign(G, static_cast<uint64_t>(trash) | (static_cast<uint64_t>(npq) << 16) | (1ull << 32));
+  if (bsched.empty()) bsched.assign(G, static_cast<uint64_t>(trash) | (static_cast<uint64_t>(npq) << 16) | (3ull << 32));
 
   // ---- 3. element -> node maps (needed by the hot blob) ----
   const int na = npq + 2;      // + sentinel + trash records
