@@ -352,14 +352,15 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
         double2 d01 = own.d01, d23 = own.d23, r = own.r;
         const double2 u = own.u, d = own.d;   // J[i,p] = [[a,b],[-b,a]](u), J[p,i] likewise (d); zero at roots
         grp_sync<G>(gidx);                                    // the previous step's Schur updates are visible
-        double2 p01 = s01, p23 = s23, pt = tt;           // child 0: registers ...
-        if (!(fl & kEschedReg0)) { p01 = make_double2(0.0, 0.0); p23 = p01; pt = p01; }
-        if (fl & kEschedLoad0) { const double2* k0 = s.node(c0); p01 = k0[A_UP]; p23 = k0[A_DN]; pt = k0[A_T]; }   // ... or smem
-        double2 q01 = make_double2(0.0, 0.0), q23 = q01, qt = q01;
-        if (fl & kEschedLoad1) { const double2* k1 = s.node(c1); q01 = k1[A_UP]; q23 = k1[A_DN]; qt = k1[A_T]; }
-        d01.x -= p01.x + q01.x; d01.y -= p01.y + q01.y;
-        d23.x -= p23.x + q23.x; d23.y -= p23.y + q23.y;
-        r.x -= pt.x + qt.x; r.y -= pt.y + qt.y;
+        // child 0: this lane's registers (chain) or shared memory (a leaf reads the all-zero sentinel record)
+        double2 p01 = s01, p23 = s23, pt = tt;
+        if (fl & kEschedLoad0) { const double2* k0 = s.node(c0); p01 = k0[A_UP]; p23 = k0[A_DN]; pt = k0[A_T]; }
+        d01.x -= p01.x; d01.y -= p01.y; d23.x -= p23.x; d23.y -= p23.y; r.x -= pt.x; r.y -= pt.y;
+        if (fl & kEschedLoad1) {                          // child 1 (branching buses only): always shared memory
+          const double2* k1 = s.node(c1);
+          const double2 q01 = k1[A_UP], q23 = k1[A_DN], qt = k1[A_T];
+          d01.x -= q01.x; d01.y -= q01.y; d23.x -= q23.x; d23.y -= q23.y; r.x -= qt.x; r.y -= qt.y;
+        }
         if (p.has_extra_children) {                      // warp-uniform: only nets with a bus of degree > 3
           const int nx = static_cast<int>(fl & 0xFFu);
 #pragma unroll 1

@@ -477,7 +477,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
         if (i < 0) { esched.push_back(static_cast<uint64_t>(trash) | (static_cast<uint64_t>(npq) << 16) |
                                       (static_cast<uint64_t>(npq) << 32) | (static_cast<uint64_t>(kEschedReg0 | kEschedIdle) << 48)); continue; }
         lane_of[i] = sidx % G; step_of[i] = cur + sidx / G;
-        uint64_t c0 = npq, c1 = npq, fl = 0;
+        uint64_t c0 = npq, c1 = npq, fl = kEschedLoad0;      // no child: child 0 = the all-zero sentinel record
         if (nchild[i] > 2) {
           c0 = cfirst[i]; c1 = cfirst[i] + 1; fl = static_cast<uint64_t>(std::min(nchild[i] - 2, 255)) | kEschedLoad0 | kEschedLoad1;
           if (nchild[i] - 2 > 255) return bail(fail(MAPDN_ERR_UNSUPPORTED, "a bus with more than 257 children"));
