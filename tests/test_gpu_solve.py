@@ -214,3 +214,34 @@ def test_degenerate_topologies():
                 assert np.abs(out["p_bus"][e].cpu().numpy() - r.p_mw).max() < 1e-8
                 assert np.abs(out["pl"][e].cpu().numpy() - r.pl_mw).max() < 1e-9
             env.close()
+
+
+def test_high_degree_hub():
+    """A bus with six children (the > 2 children path of the sweeps: extras gathered from shared memory) and a
+    second hub further down, all lane counts."""
+    from oracle.pandapower_nr import PandapowerEquivalent
+    rng = np.random.default_rng(9)
+    f, t = [0], [1]                        # slack 0 - hub 1
+    nxt = 2
+    for k in range(6):                     # six feeders of three buses off the hub
+        f += [1, nxt, nxt + 1]; t += [nxt, nxt + 1, nxt + 2]; nxt += 3
+    hub2 = 4                               # a second hub on the first feeder: four more leaves
+    for k in range(4):
+        f.append(hub2); t.append(nxt); nxt += 1
+    n = nxt
+    net = NetDesc(base_mva=1.0, n_bus=n, slack_bus=0, slack_vm=1.0, br_from=f, br_to=t,
+                  br_r=rng.uniform(0.002, 0.01, n - 1), br_x=rng.uniform(0.002, 0.01, n - 1), load_bus=np.arange(1, n),
+                  sgen_bus=[3, 10, n - 1], sgen_zone=[1, 1, 1], bus_zone=[0] + [1] * (n - 1))
+    pf = PandapowerEquivalent(net)
+    B = 6
+    pl = rng.uniform(0.0, 0.06, (B, n - 1)); ql = 0.4 * pl
+    pv = rng.uniform(0.0, 0.3, (B, 3)); q = rng.uniform(-0.1, 0.1, (B, 3))
+    for lanes in (4, 8, 32, 64):
+        env = _env(net, lanes_per_env=lanes)
+        out = env.solve(pl, ql, pv, q)
+        for e in range(B):
+            r = pf.runpp(pl[e], ql[e], pv[e], q[e])
+            assert r.converged and bool(out["converged"][e]) and int(out["iterations"][e]) == r.iterations
+            assert np.abs(out["vm"][e].cpu().numpy() - r.vm_pu).max() < VTOL
+            assert np.abs(out["pl"][e].cpu().numpy() - r.pl_mw).max() < 1e-9
+        env.close()
