@@ -32,6 +32,23 @@ static mapdn_status fail(mapdn_status st, const std::string& msg) {
       return fail(MAPDN_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
   } while (0)
 
+// Every entry point runs on the handle's device and leaves the calling thread's current device as it found it
+// (the caller -- PyTorch, CuPy -- tracks the current device through the CUDA runtime).
+struct DeviceGuard {
+  int prev = -1, dev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) : dev(device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+  }
+  ~DeviceGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define MAPDN_ON_DEVICE(device)          \
+  DeviceGuard _device_guard(device);     \
+  MAPDN_CUDA(_device_guard.err)
+
 // ------------------------------------------------------------------------------------------------
 // Ybus assembly on the device (PYPOWER makeYbus). Runs once per handle: the
 // topology never changes between env steps (the reference rebuilds Ybus inside every pp.runpp).
@@ -261,7 +278,7 @@ const char* mapdn_last_error(void) { return g_last_error.c_str(); }
 
 mapdn_status mapdn_destroy(mapdn_env* e) {
   if (!e) return MAPDN_OK;
-  cudaSetDevice(e->device);
+  DeviceGuard guard(e->device);
   for (void* d : e->allocs) cudaFree(d);
   delete e;
   return MAPDN_OK;
@@ -297,7 +314,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
         !prof->load_q_std || !prof->s_max || prof->n_rows < 2 || prof->steps_per_hour < 1)
       return fail(MAPDN_ERR_INVALID, "incomplete profile description");
   }
-  MAPDN_CUDA(cudaSetDevice(device));
+  MAPDN_ON_DEVICE(device);
   mapdn_env* e = new (std::nothrow) mapdn_env();
   if (!e) return fail(MAPDN_ERR_NOMEM, "out of host memory");
   e->device = device;
@@ -832,7 +849,7 @@ mapdn_status mapdn_reset(mapdn_env* e, const int32_t* start_dhi_dev, const uint8
                          double* obs_dev, double* state_dev, void* stream) {
   if (!e) return fail(MAPDN_ERR_INVALID, "null handle");
   if (!e->base.prof_pv) return fail(MAPDN_ERR_INVALID, "handle was created without a profile store");
-  MAPDN_CUDA(cudaSetDevice(e->device));
+  MAPDN_ON_DEVICE(e->device);
   Params p = e->base;
   p.start_dhi = start_dhi_dev; p.mask = mask_dev; p.add_noise = add_noise; p.obs = obs_dev; p.state = state_dev;
   return launch_env_kernel(e, MODE_RESET, p, static_cast<cudaStream_t>(stream));
@@ -842,7 +859,7 @@ mapdn_status mapdn_step(mapdn_env* e, const double* actions_dev, int32_t add_noi
                         uint8_t* terminated_dev, double* info_dev, double* obs_dev, void* stream) {
   if (!e || !actions_dev || !reward_dev || !terminated_dev) return fail(MAPDN_ERR_INVALID, "null argument");
   if (!e->base.prof_pv) return fail(MAPDN_ERR_INVALID, "handle was created without a profile store");
-  MAPDN_CUDA(cudaSetDevice(e->device));
+  MAPDN_ON_DEVICE(e->device);
   Params p = e->base;
   p.actions = actions_dev; p.add_noise = add_noise; p.reward = reward_dev; p.term = terminated_dev;
   p.info = info_dev; p.obs = obs_dev;
@@ -852,7 +869,7 @@ mapdn_status mapdn_step(mapdn_env* e, const double* actions_dev, int32_t add_noi
 mapdn_status mapdn_step_host(mapdn_env* e, const double* actions_host, int32_t add_noise, double* reward_host,
                              uint8_t* terminated_host, double* info_host, double* obs_host, void* stream) {
   if (!e || !actions_host || !reward_host || !terminated_host) return fail(MAPDN_ERR_INVALID, "null argument");
-  MAPDN_CUDA(cudaSetDevice(e->device));
+  MAPDN_ON_DEVICE(e->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t B = e->dims.batch, ng = e->dims.n_sgen, od = e->dims.obs_dim;
   MAPDN_CUDA(cudaMemcpyAsync(e->d_stage_actions, actions_host, B * ng * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -871,7 +888,7 @@ mapdn_status mapdn_step_f32obs(mapdn_env* e, const double* actions_dev, int32_t 
                                uint8_t* terminated_dev, double* info_dev, float* obs_dev, void* stream) {
   if (!e || !actions_dev || !reward_dev || !terminated_dev) return fail(MAPDN_ERR_INVALID, "null argument");
   if (!e->base.prof_pv) return fail(MAPDN_ERR_INVALID, "handle was created without a profile store");
-  MAPDN_CUDA(cudaSetDevice(e->device));
+  MAPDN_ON_DEVICE(e->device);
   Params p = e->base;
   p.actions = actions_dev; p.add_noise = add_noise; p.reward = reward_dev; p.term = terminated_dev;
   p.info = info_dev; p.obs = nullptr; p.obs32 = obs_dev;
@@ -881,7 +898,7 @@ mapdn_status mapdn_step_f32obs(mapdn_env* e, const double* actions_dev, int32_t 
 mapdn_status mapdn_step_host_f32obs(mapdn_env* e, const double* actions_host, int32_t add_noise, double* reward_host,
                                     uint8_t* terminated_host, double* info_host, float* obs_host, void* stream) {
   if (!e || !actions_host || !reward_host || !terminated_host) return fail(MAPDN_ERR_INVALID, "null argument");
-  MAPDN_CUDA(cudaSetDevice(e->device));
+  MAPDN_ON_DEVICE(e->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t B = e->dims.batch, ng = e->dims.n_sgen, od = e->dims.obs_dim;
   float* d_obs32 = reinterpret_cast<float*>(e->d_stage_obs);          // the fp64 staging buffer is large enough
@@ -899,7 +916,7 @@ mapdn_status mapdn_step_host_f32obs(mapdn_env* e, const double* actions_host, in
 
 mapdn_status mapdn_get_obs(mapdn_env* e, double* obs_dev, void* stream) {
   if (!e || !obs_dev) return fail(MAPDN_ERR_INVALID, "null argument");
-  MAPDN_CUDA(cudaSetDevice(e->device));
+  MAPDN_ON_DEVICE(e->device);
   Params p = e->base;
   p.obs = obs_dev;
   const long long tot = static_cast<long long>(p.nb) * p.n_sgen * p.obs_dim;
@@ -911,7 +928,7 @@ mapdn_status mapdn_get_obs(mapdn_env* e, double* obs_dev, void* stream) {
 
 mapdn_status mapdn_get_state(mapdn_env* e, double* state_dev, void* stream) {
   if (!e || !state_dev) return fail(MAPDN_ERR_INVALID, "null argument");
-  MAPDN_CUDA(cudaSetDevice(e->device));
+  MAPDN_ON_DEVICE(e->device);
   Params p = e->base;
   p.state = state_dev;
   const long long tot = static_cast<long long>(p.nb) * p.state_dim;
@@ -923,7 +940,7 @@ mapdn_status mapdn_get_state(mapdn_env* e, double* state_dev, void* stream) {
 
 mapdn_status mapdn_get_field(mapdn_env* e, int32_t field, double* out_dev, void* stream) {
   if (!e || !out_dev) return fail(MAPDN_ERR_INVALID, "null argument");
-  MAPDN_CUDA(cudaSetDevice(e->device));
+  MAPDN_ON_DEVICE(e->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const Params& p = e->base;
   const long long B = p.nb;
@@ -963,7 +980,7 @@ mapdn_status mapdn_solve(mapdn_env* e, int32_t nb, const double* p_load, const d
                          int32_t* iters, uint8_t* converged, void* stream) {
   if (!e || nb < 1 || !p_sgen || !q_sgen || (e->dims.n_load > 0 && (!p_load || !q_load)))
     return fail(MAPDN_ERR_INVALID, "null argument");
-  MAPDN_CUDA(cudaSetDevice(e->device));
+  MAPDN_ON_DEVICE(e->device);
   Params p = e->base;
   p.nb = nb;
   p.in_pl = p_load; p.in_ql = q_load; p.in_pv = p_sgen; p.in_q = q_sgen;

@@ -332,3 +332,23 @@ def test_batched_history_stacking():
     env.reset(mask=mask)
     st = env.get_obs_stacked()
     assert float(st[0, :, :100].abs().max()) == 0.0 and float(st[1, :, :100].abs().max()) > 0.0
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_calls_leave_the_current_device_alone():
+    """A handle bound to cuda:1 works while the caller's current device stays cuda:0 (every C-ABI entry point
+    restores the device it found)."""
+    net, prof = cases.make_case("case33"), cases.make_profiles("case33", n_days=4)
+    torch.cuda.set_device(0)
+    e0 = _make(net, prof, dict(seed=2), batch=8)
+    from mapdn_b200.env import BatchedVoltageControl
+    e1 = BatchedVoltageControl(net, prof, dict(seed=2), batch=8, device=1)
+    assert torch.cuda.current_device() == 0
+    e0.reset(); e1.reset()
+    a = torch.full((8, 6), 0.3, dtype=torch.float64)
+    r0, _, _ = e0.step(a.to("cuda:0"))
+    r1, _, _ = e1.step(a.to("cuda:1"))
+    assert torch.cuda.current_device() == 0
+    assert torch.equal(r0.cpu(), r1.cpu())
+    e1.close()
+    assert torch.cuda.current_device() == 0
