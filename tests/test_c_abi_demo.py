@@ -86,4 +86,4 @@ def test_demo_matches_the_python_binding(built_lib):
         assert abs(rs - float(rew.cpu().numpy().sum())) < 1e-12 * max(1.0, abs(rs))
         assert abs(os_ - float(env.obs.cpu().numpy().sum())) < 1e-12 * max(1.0, abs(os_))
         assert int(got[k][4]) == int(term.sum().item())
-    assert lines[-1] == "launches 11"       # one reset + ten fused steps
+    assert lines[-1] == f"launches {env.launch_count}"   # Ybus assembly at create + one reset + ten fused steps
