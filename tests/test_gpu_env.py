@@ -352,3 +352,51 @@ def test_calls_leave_the_current_device_alone():
     assert torch.equal(r0.cpu(), r1.cpu())
     e1.close()
     assert torch.cuda.current_device() == 0
+
+
+def _barrier_torch(kind, v):
+    """Reference voltage_barrier/{l1,l2,bowl}.py restated on tensors (independent of the oracle and of the kernel)."""
+    d = (v - 1.0).abs()
+    if kind == "l1":
+        return d
+    if kind == "l2":
+        return 2.0 * (v - 1.0) ** 2
+    pdf = torch.exp(-0.5 * ((v - 1.0) / 0.1) ** 2) / (0.1 * (2.0 * torch.pi) ** 0.5)
+    return torch.where(d > 0.05, 2.0 * d - 0.095, -0.01 * pdf + 0.04)
+
+
+@pytest.mark.parametrize("name,batch", [("case33", 4096), ("case141", 2048), ("case322", 1024)])
+def test_full_size_step_properties(name, batch):
+    """BASELINE.json configs 1-3 at full batch: the fused step's outputs satisfy the reference's definitions when
+    recomputed from the solved voltages with plain tensor code (reference _clip_reactive_power :568-572,
+    _calc_reward :574-623), and the trajectories do not depend on how the batch is sharded."""
+    sc = cases.SCENARIOS[name]
+    net, prof = cases.make_case(name), cases.make_profiles(name)
+    args = dict(voltage_barrier_type=sc["barrier"], action_scale=sc["action_scale"], seed=11)
+    env = _make(net, prof, args, batch=batch)
+    half = [_make(net, prof, args, batch=batch // 2), _make(net, prof, args, batch=batch // 2, env_id_offset=batch // 2)]
+    env.reset()
+    for h in half:
+        h.reset()
+    s_max = torch.tensor(prof.s_max, device=env.device)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    for _ in range(3):
+        a = (torch.rand(batch, env.n_agents, generator=g, dtype=torch.float64) * 2 - 1) * sc["action_scale"]
+        a = a.to(env.device)
+        p_before = env.get_field("p_sgen")
+        r, term, info = env.step(a)
+        vm, q = env.get_field("vm"), env.get_field("q_sgen")
+        ok = info[:, 10] == 0                                     # destroy flag: the reward definition below holds
+        assert ok.float().mean().item() > 0.99
+        assert torch.allclose(q, a * torch.sqrt(s_max ** 2 - p_before ** 2), rtol=0, atol=1e-12)
+        want = -(0.1 * q.abs().mean(dim=1) + _barrier_torch(sc["barrier"], vm).mean(dim=1))
+        assert (r - want)[ok].abs().max().item() < 1e-10
+        out = ((vm < 0.95) | (vm > 1.05)).double().mean(dim=1)
+        assert (info[:, 0] - out)[ok].abs().max().item() < 1e-12
+        assert (info[:, 5] - vm.mean(dim=1))[ok].abs().max().item() < 1e-12
+        assert (info[:, 8] - env.get_field("line_loss").sum(dim=1))[ok].abs().max().item() < 1e-12
+        assert (info[:, 9] - q.abs().mean(dim=1))[ok].abs().max().item() < 1e-12
+        assert not term.any()
+        rh = torch.cat([h.step(a[i * (batch // 2):(i + 1) * (batch // 2)].contiguous())[0] for i, h in enumerate(half)])
+        assert torch.equal(rh, r)
+        assert torch.equal(torch.cat([h.obs for h in half]), env.obs)
