@@ -122,14 +122,52 @@ def run_reference(args):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons DURING the timed region: NVML polled every ~2 ms from a thread (the timed region of
+    the default run is only tens of ms long); `nvidia-smi -lms 50` is the fallback when NVML is not usable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASON_BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20),
+                   ("hw_thermal_slowdown", 0x40))            # nvmlClocksEventReason* bit masks
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.samples = index, [], None, None, []
+        self._stop = threading.Event()
+
+    def _nvml_open(self):
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        h = None
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)); int(reasons(h))      # probe once
+        return pynvml, h, reasons, mx
+
+    def _poll(self):
+        pynvml, h, reasons, _ = self.nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                     int(reasons(h))))
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            self.nvml = self._nvml_open()
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True,
@@ -144,6 +182,17 @@ class ClockSampler:
             self.rows.append((time.perf_counter(), ln.strip()))
 
     def stop(self, t0, t1):
+        if self.nvml is not None:
+            self._stop.set()
+            self.th.join(timeout=1.0)
+            rows = [r for r in self.samples if t0 <= r[0] <= t1] or self.samples[-3:]
+            if rows:
+                bits = 0
+                for r in rows:
+                    bits |= r[2]
+                return dict(sm_mhz=float(np.median([r[1] for r in rows])), sm_max_mhz=self.nvml[3],
+                            reasons=sorted(nm for nm, b in self.REASON_BITS if bits & b), samples=len(rows), source="nvml")
+            return None
         if self.proc is None:
             return None
         time.sleep(0.12)
@@ -161,7 +210,8 @@ class ClockSampler:
                     reasons.add(nm)
         if not sm:
             return None
-        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm),
+                    source="nvidia-smi")
 
 
 # ------------------------------------------------------------------------------------------------
