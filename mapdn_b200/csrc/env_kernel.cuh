@@ -226,7 +226,7 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
 struct Hot {
   const double2 *yup, *ydn, *yii, *ysl;
   const uint64_t *ndesc, *esched, *bsched;
-  const uint16_t *lptr, *lidx, *sptr, *sidx, *xptr, *xidx, *node_of_bus, *bus_of_node, *obs_off, *line_nodes;
+  const uint16_t *lptr, *lidx, *sptr, *sidx, *xptr, *xidx, *node_of_bus, *obs_off, *line_nodes;
   const double* line_c;
   const uint16_t *nbr_ptr, *nbr_idx;   // meshed nets (dense solver) only
   const double2* nbr_y;
@@ -582,7 +582,6 @@ __global__ void __launch_bounds__(G > 32 ? 544 : 160) env_kernel(const __grid_co
   h.xptr = reinterpret_cast<const uint16_t*>(smem_raw + hl.xptr);
   h.xidx = reinterpret_cast<const uint16_t*>(smem_raw + hl.xidx);
   h.node_of_bus = reinterpret_cast<const uint16_t*>(smem_raw + hl.node_of_bus);
-  h.bus_of_node = reinterpret_cast<const uint16_t*>(smem_raw + hl.bus_of_node);
   h.obs_off = reinterpret_cast<const uint16_t*>(smem_raw + hl.obs_off);
   h.line_nodes = reinterpret_cast<const uint16_t*>(smem_raw + hl.line_nodes);
   h.line_c = reinterpret_cast<const double*>(smem_raw + hl.line_c);
@@ -821,21 +820,24 @@ __global__ void __launch_bounds__(G > 32 ? 544 : 160) env_kernel(const __grid_co
     }
     grp_sync<G>(gidx);
     PROF(8)
-    // One pass over the node records (slack sentinel included): res_bus columns (BP), the "demand" columns of
-    // get_obs (OP = BP + sgens of the bus's own zone, reference :238-244), result write-back and the voltage
-    // statistics of the reward (reference _calc_reward :584-596, :610)
-    double cnt_lo = 0, cnt_hi = 0, sum_dev = 0, sum_v = 0, max_drop = 0, max_rise = 0, sum_bar = 0;
-    const double v_ref = 0.5 * (p.v_lower + p.v_upper);
-#pragma unroll 4
+    // res_bus columns per node (BP) and the "demand" columns of get_obs (OP = BP + sgens of the bus's own zone)
     for (int i = gl; i <= npq; i += G) {
       double2* nd = s.node(i);
-      const double2 sp = nd[A_SP], vv = nd[A_VV];
-      const int b = h.bus_of_node[i];
+      const double2 sp = nd[A_SP];
       const double2 bp = make_double2(-sp.x * p.base_mva, -sp.y * p.base_mva);
       double2 op = bp;
 #pragma unroll 1
       for (int t = h.xptr[i], te = h.xptr[i + 1]; t < te; ++t) { const int g = h.xidx[t]; op.x += s.pv[g]; op.y += s.q[g]; }
       nd[A_BP] = bp; nd[A_OP] = op;
+    }
+    grp_sync<G>(gidx);
+    // per-bus results + voltage statistics (reference _calc_reward :584-596, :610)
+    double cnt_lo = 0, cnt_hi = 0, sum_dev = 0, sum_v = 0, max_drop = 0, max_rise = 0, sum_bar = 0;
+    const double v_ref = 0.5 * (p.v_lower + p.v_upper);
+#pragma unroll 4
+    for (int b = gl; b < n; b += G) {
+      const double2* nd = s.node(h.node_of_bus[b]);
+      const double2 vv = nd[A_VV], bp = nd[A_BP];
       const double v = vv.x, th = vv.y;
       if (MODE == MODE_SOLVE) {
         if (valid) {
@@ -859,7 +861,6 @@ __global__ void __launch_bounds__(G > 32 ? 544 : 160) env_kernel(const __grid_co
         }
       }
     }
-    grp_sync<G>(gidx);
     // line losses: res_line.pl_mw = Re(Sf + St), 4 static coefficients per line
     double sum_pl = 0.0;
     {

@@ -44,7 +44,6 @@ struct HotLayout {        // byte offsets inside the hot static blob (staged int
   int sptr, sidx;         // uint16 [npq+2], [n_sgen]: node -> sgens
   int xptr, xidx;         // uint16 [npq+2], [<=n_sgen]: node -> sgens of the node's own zone (obs add-back)
   int node_of_bus;        // uint16 [n_bus]: bus -> node (slack -> npq)
-  int bus_of_node;        // uint16 [npq+1]: node -> bus (entry npq = the slack bus)
   int obs_off;            // uint16 [n_sgen*obs_dim]: obs entry -> double offset inside the env slab
   int line_nodes;         // uint16 [2*n_line]: from / to node of every line (npq = slack)
   int line_c;             // double [4*n_line]: loss coefficients (see mapdn_b200.cu)

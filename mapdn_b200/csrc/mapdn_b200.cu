@@ -670,7 +670,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     hl.lptr = take(2 * lptr.size()); hl.lidx = take(2 * lidx.size());
     hl.sptr = take(2 * sptr.size()); hl.sidx = take(2 * sidx.size());
     hl.xptr = take(2 * xptr.size()); hl.xidx = take(2 * std::max<size_t>(1, xidx.size()));
-    hl.node_of_bus = take(2 * n); hl.bus_of_node = take(2 * (npq + 1)); hl.obs_off = take(2 * obs_off.size());
+    hl.node_of_bus = take(2 * n); hl.obs_off = take(2 * obs_off.size());
     hl.line_nodes = take(2 * std::max<size_t>(1, line_nodes.size())); hl.line_c = take(8 * std::max<size_t>(1, line_c.size()));
     hl.nbr_ptr = take(2 * nbr_ptr.size()); hl.nbr_idx = take(2 * std::max<size_t>(1, nbr_idx.size()));
     hl.nbr_y = take(8 * std::max<size_t>(2, nbr_y.size()));
@@ -712,9 +712,6 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     if (!xidx.empty()) std::memcpy(hot.data() + hl.xidx, xidx.data(), 2 * xidx.size());
     uint16_t* nob = reinterpret_cast<uint16_t*>(hot.data() + hl.node_of_bus);
     for (int b = 0; b < n; ++b) nob[b] = static_cast<uint16_t>(node_of_bus[b]);
-    uint16_t* bon = reinterpret_cast<uint16_t*>(hot.data() + hl.bus_of_node);
-    for (int i = 0; i < npq; ++i) bon[i] = static_cast<uint16_t>(order[i]);
-    bon[npq] = static_cast<uint16_t>(slack);
     std::memcpy(hot.data() + hl.obs_off, obs_off.data(), 2 * obs_off.size());
     std::memcpy(hot.data() + hl.nbr_ptr, nbr_ptr.data(), 2 * nbr_ptr.size());
     if (!nbr_idx.empty()) {
