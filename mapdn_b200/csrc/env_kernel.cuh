@@ -557,7 +557,7 @@ __device__ __forceinline__ double clip_q(double a, double pv, double smax) {
 }
 
 template <int G, int MODE, bool DENSE = false>
-__global__ void __launch_bounds__(G > 32 ? 544 : 160) env_kernel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_constant__ Params p) {
   static_assert(!DENSE || G == 32, "the dense fallback uses one warp per env");
   static_assert(G == 4 || G == 8 || G == 16 || G == 32 || G == 64 || G == 128, "unsupported group size");
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -591,7 +591,8 @@ __global__ void __launch_bounds__(G > 32 ? 544 : 160) env_kernel(const __grid_co
 
   // MODE_STEP: the last warp of the CTA is a helper that draws the next profile rows (+ noise) of the CTA's
   // envs while the solver warps run the Newton iteration (the two only meet at two named barriers)
-  const int n_solver_threads = blockDim.x - ((MODE == MODE_STEP) ? 32 : 0);
+  const int n_helper_threads = (MODE == MODE_STEP) ? p.helper_threads : 0;
+  const int n_solver_threads = blockDim.x - n_helper_threads;
   const bool is_helper = (MODE == MODE_STEP) && threadIdx.x >= n_solver_threads;
   const int hl_bytes = p.hot_layout.bytes;
   const int gl = threadIdx.x % G;
@@ -620,7 +621,7 @@ __global__ void __launch_bounds__(G > 32 ? 544 : 160) env_kernel(const __grid_co
       named_bar_sync(1, blockDim.x);                   // the solvers have read the current rows
       const int n_elem = ng + 2 * nl, n_pair = (n_elem + 1) / 2;
       const int hl = threadIdx.x - n_solver_threads;
-      for (int w = hl; w < epb * n_pair; w += 32) {
+      for (int w = hl; w < epb * n_pair; w += n_helper_threads) {
         const int e = w / n_pair, m = w - e * n_pair, env_h = base + e;
         if (env_h >= p.nb) continue;
         const int steps_h = p.steps[env_h];

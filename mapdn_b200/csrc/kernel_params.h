@@ -62,6 +62,7 @@ struct Params {
   int n_bus, npq, n_load, n_sgen, n_line, n_lev, obs_dim, state_dim, n_slack_adj, slack_bus;
   int n_esteps, n_bsteps, has_extra_children;   // schedule lengths (for the handle's G); any bus with > 2 children
   int nb;                 // envs processed by this launch
+  int helper_threads;     // MODE_STEP: threads of the helper warps behind the solver threads of a CTA
   int env_stride2;        // double2 elements of smem per env
   int pvq_off2;           // double2 offset of the sgen (pv | q) block inside the env slab
   int scratch_off2;       // double2 offset of the scratch region (prologue staging / next-row prefetch)

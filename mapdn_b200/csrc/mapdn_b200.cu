@@ -159,7 +159,7 @@ struct mapdn_env {
   mapdn_dims dims{};
   Params base{};                       // static + state pointers; io fields filled per call
   std::vector<void*> allocs;           // everything cudaMalloc'ed
-  int G = 8, threads = 128, epb = 16, smem = 0, max_blocks = 0;
+  int G = 8, threads = 128, epb = 16, smem = 0, max_blocks = 0, helper_threads = 32;
   bool dense = false;                  // meshed net: dense-LU fallback solver
   long long launches = 0;
   // Ybus pieces kept for the test hook
@@ -249,7 +249,8 @@ mapdn_status launch_env_kernel(mapdn_env* e, int mode, Params& p, cudaStream_t s
   cudaMemset(d_prof, 0, 12 * sizeof(long long));
   p.prof = d_prof;
 #endif
-  fn<<<grid, e->threads + (mode == MODE_STEP ? 32 : 0), e->smem, st>>>(p);   // MODE_STEP: + 1 helper warp
+  p.helper_threads = e->helper_threads;
+  fn<<<grid, e->threads + (mode == MODE_STEP ? e->helper_threads : 0), e->smem, st>>>(p);   // MODE_STEP: + helper warps
   MAPDN_CUDA(cudaGetLastError());
   e->launches++;
 #ifdef MAPDN_PROFILE
@@ -737,20 +738,45 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   // as many multi-warp envs as fit (<= 512 solver threads)
   int epb = (G <= 16) ? 2 * unit : 4 * unit;
   if (G > 32) while (epb > 1 && epb * G > 512) --epb;
+  // Few-round batches (the BASELINE.json configs): one CTA per SM holding ceil(B / (SMs * rounds)) envs balances the
+  // SMs exactly (case33 x 4096: 147 CTAs of 28 envs instead of 512 of 8, i.e. 7 instead of up to 8 solver warps on
+  // the busiest SM; case141 x 2048: 2 rounds of 7). Many-round batches keep several small CTAs per SM.
+  {
+    auto fits = [&](int c) { return smem_for(c) <= max_smem && c * G <= (G <= 32 ? 256 : 512); };
+    const int n_sm = dp.multiProcessorCount;
+    for (int r = 1; r <= 3; ++r) {
+      int c = (cfg->batch + n_sm * r - 1) / (n_sm * r);
+      c = (c + unit - 1) / unit * unit;
+      if (fits(c)) { epb = std::max(epb, c); break; }
+    }
+  }
   if (const char* ov = getenv("MAPDN_EPB")) epb = std::max(unit, atoi(ov) / unit * unit);   // tuning override
-  while (epb > unit && smem_for(epb) > max_smem) epb -= unit;
+  while (epb > unit && (smem_for(epb) > max_smem || (G <= 32 && epb * G > 256))) epb -= unit;
   if (smem_for(epb) > max_smem)
     return bail(fail(MAPDN_ERR_UNSUPPORTED, "network too large for the shared-memory resident solver (" +
                                                 std::to_string(smem_for(epb)) + " B needed)"));
   e->dense = meshed;
   e->G = G; e->threads = epb * G; e->epb = epb; e->smem = static_cast<int>(smem_for(epb));
+  {   // helper warps (next profile rows + noise, concurrent with the Newton iteration): one per 256 Box-Muller pairs of a
+      // CTA round, at most 4 -- a single warp was the critical path of case322 (197 -> 169 us with two)
+    const int n_pair = (ng + 2 * nl + 1) / 2;
+    e->helper_threads = 32 * std::min(4, std::max(1, (epb * n_pair + 255) / 256));
+  }
+  if (const char* ov = getenv("MAPDN_HELPERS")) e->helper_threads = 32 * std::min(4, std::max(1, atoi(ov)));   // tuning override
   for (int mode = 0; mode < 3; ++mode) {
     KernelFn fn = kernel_for(G, mode, meshed);
-    TRY_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem));
+    // the attribute belongs to the function, not to the handle: always allow the device maximum, so that creating a
+    // second handle with a smaller footprint cannot break the launches of the first
+    cudaFuncAttributes fa{};
+    TRY_CUDA(cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(fn)));
+    const int dyn_max = static_cast<int>(max_smem - fa.sharedSizeBytes);        // opt-in limit minus the static part
+    if (e->smem > dyn_max)
+      return bail(fail(MAPDN_ERR_UNSUPPORTED, "network too large for the shared-memory resident solver"));
+    TRY_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max));
   }
   {
     int per_sm = 0;
-    TRY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel_for(G, MODE_STEP, meshed), e->threads + 32, e->smem));
+    TRY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel_for(G, MODE_STEP, meshed), e->threads + e->helper_threads, e->smem));
     e->max_blocks = std::max(1, per_sm) * dp.multiProcessorCount;
     if (meshed) e->max_blocks = std::min(e->max_blocks, 2 * dp.multiProcessorCount);   // bounds the dense workspace
   }

@@ -400,3 +400,18 @@ def test_full_size_step_properties(name, batch):
         rh = torch.cat([h.step(a[i * (batch // 2):(i + 1) * (batch // 2)].contiguous())[0] for i, h in enumerate(half)])
         assert torch.equal(rh, r)
         assert torch.equal(torch.cat([h.obs for h in half]), env.obs)
+
+
+def test_handles_with_different_footprints_coexist():
+    """The dynamic shared-memory limit is a per-function attribute: creating a handle with a smaller per-CTA footprint
+    (smaller batch -> fewer envs per CTA) must not break the launches of an older, larger one."""
+    net, prof = cases.make_case("case33"), cases.make_profiles("case33", n_days=4)
+    big = _make(net, prof, dict(seed=1), batch=4096)
+    small = _make(net, prof, dict(seed=1), batch=8)
+    assert big.dims["smem_bytes"] > small.dims["smem_bytes"]
+    big.reset(); small.reset()
+    a = torch.zeros(4096, 6, dtype=torch.float64, device=big.device)
+    r_big, _, _ = big.step(a)
+    r_small, _, _ = small.step(a[:8].contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(r_big[:8], r_small)             # same env ids, same seed: the CTA shape does not change results
