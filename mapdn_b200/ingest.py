@@ -22,7 +22,8 @@ import numpy as np
 
 from .network import NetDesc, ProfileDesc
 
-__all__ = ["load_profiles", "load_network", "load_scenario", "net_from_tables", "read_model_pickle"]
+__all__ = ["load_profiles", "load_network", "load_scenario", "net_from_tables", "read_model_pickle",
+           "save_scenario_npz", "load_scenario_npz", "net_to_json", "net_from_json", "SCENARIO_NPZ"]
 
 
 # --------------------------------------------------------------------------------------------------
@@ -251,10 +252,75 @@ def load_network(path: str) -> NetDesc:
     return net_from_tables(read_model_pickle(path), name=os.path.basename(os.path.dirname(path)) or "net")
 
 
+# --------------------------------------------------------------------------------------------------
+# Export format: the per-unit network as JSON, a whole scenario as one NPZ
+# --------------------------------------------------------------------------------------------------
+SCENARIO_NPZ = "scenario.npz"
+_NET_SCALARS = ("base_mva", "n_bus", "slack_bus", "slack_vm", "slack_va_deg", "vm_init", "name")
+_NET_ARRAYS = ("br_from", "br_to", "br_r", "br_x", "br_b", "br_g", "br_tap", "br_shift", "br_status", "br_is_line",
+               "bus_gs", "bus_bs", "bus_zone", "load_bus", "load_scaling", "sgen_bus", "sgen_zone", "sgen_scaling")
+
+
+def net_to_json(net: NetDesc) -> str:
+    """The static network (what ``_pd2ppc`` derives from ``model.p``) as a JSON document; floats round-trip exactly
+    (``repr`` precision)."""
+    import json
+    d = {k: getattr(net, k) for k in _NET_SCALARS}
+    d.update({k: np.asarray(getattr(net, k)).tolist() for k in _NET_ARRAYS})
+    d["zone_names"] = list(net.zone_names)
+    d["format"] = "mapdn_b200.net/1"
+    return json.dumps(d)
+
+
+def net_from_json(text: str) -> NetDesc:
+    import json
+    d = json.loads(text)
+    if d.pop("format", None) != "mapdn_b200.net/1":
+        raise ValueError("not a mapdn_b200 network document")
+    return NetDesc(**d)
+
+
+def save_scenario_npz(path: str, net: NetDesc, prof: ProfileDesc) -> str:
+    """One compressed file with the network (JSON) and the three profile tables *before* ``pv_scale`` /
+    ``demand_scale`` - parsing three years of 3-minute CSV rows takes tens of seconds, this loads in well under one.
+    ``path`` may be a directory (-> ``<path>/scenario.npz``, picked up by :func:`load_scenario`)."""
+    if os.path.isdir(path):
+        path = os.path.join(path, SCENARIO_NPZ)
+    np.savez_compressed(path, net_json=np.array(net_to_json(net)), pv=prof.pv, load_p=prof.load_p, load_q=prof.load_q,
+                        steps_per_hour=np.int64(prof.steps_per_hour), n_days=np.int64(prof.n_days))
+    return path
+
+
+def load_scenario_npz(path: str, pv_scale: float = 1.0, demand_scale: float = 1.0) -> Tuple[NetDesc, ProfileDesc]:
+    with np.load(path, allow_pickle=False) as z:
+        net = net_from_json(str(z["net_json"]))
+        prof = ProfileDesc(pv=z["pv"] * pv_scale, load_p=z["load_p"] * demand_scale, load_q=z["load_q"] * demand_scale,
+                           steps_per_hour=int(z["steps_per_hour"]), n_days=int(z["n_days"]))
+    return net, prof
+
+
 def load_scenario(data_path: str, pv_scale: float = 1.0, demand_scale: float = 1.0) -> Tuple[NetDesc, ProfileDesc]:
-    """``data_path`` as in the reference's env_args (a directory with model.p and the three CSVs)."""
+    """``data_path`` as in the reference's env_args (a directory with model.p and the three CSVs). A
+    ``scenario.npz`` written by :func:`save_scenario_npz` (``python -m mapdn_b200.ingest <data_path>``) takes
+    precedence when it is at least as new as the four source files."""
+    npz = os.path.join(data_path, SCENARIO_NPZ)
+    sources = [os.path.join(data_path, f) for f in ("model.p", "pv_active.csv", "load_active.csv", "load_reactive.csv")]
+    if os.path.isfile(npz) and all((not os.path.exists(f)) or os.path.getmtime(f) <= os.path.getmtime(npz) for f in sources):
+        net, prof = load_scenario_npz(npz, pv_scale, demand_scale)
+        if prof.pv.shape[1] != net.n_sgen or prof.load_p.shape[1] != net.n_load:
+            raise ValueError("profile columns do not match the net's sgen / load tables")
+        return net, prof
     net = load_network(os.path.join(data_path, "model.p"))
     prof = load_profiles(data_path, pv_scale, demand_scale)
     if prof.pv.shape[1] != net.n_sgen or prof.load_p.shape[1] != net.n_load:
         raise ValueError("profile columns do not match the net's sgen / load tables")
     return net, prof
+
+
+if __name__ == "__main__":          # python -m mapdn_b200.ingest <data_path> [out.npz]
+    import sys
+    if len(sys.argv) < 2:
+        sys.exit("usage: python -m mapdn_b200.ingest <scenario directory> [out.npz]")
+    _net, _prof = load_scenario(sys.argv[1])
+    _out = save_scenario_npz(sys.argv[2] if len(sys.argv) > 2 else sys.argv[1], _net, _prof)
+    print(f"{_out}: {_net.n_bus} buses, {_net.n_load} loads, {_net.n_sgen} sgens, {_prof.n_rows} rows")

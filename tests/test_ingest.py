@@ -107,6 +107,23 @@ def test_model_pickle_layouts_and_csv(tmp_path):
     assert np.allclose(make_ybus(nets[0])[0].toarray(), make_ybus(nets[1])[0].toarray())
     raw = pd.read_csv(p1 / "pv_active.csv").iloc[:, 1:].to_numpy()
     assert np.allclose(ingest.load_profiles(str(p1), pv_scale=2.0).pv, 2.0 * raw)
+    # one-off conversion (python -m mapdn_b200.ingest <dir>): load_scenario then reads scenario.npz, as long as it is
+    # not older than the source files
+    import subprocess, sys, time
+    from conftest import ROOT
+    net0, prof0 = ingest.load_scenario(str(p1))
+    r = subprocess.run([sys.executable, "-m", "mapdn_b200.ingest", str(p1)], capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0 and "scenario.npz" in r.stdout, r.stderr
+    os.rename(p1 / "model.p", p1 / "model.p.off")                       # proves the NPZ is what gets read
+    net1, prof1 = ingest.load_scenario(str(p1))
+    assert np.array_equal(prof1.pv, prof0.pv) and np.array_equal(net1.br_r, net0.br_r)
+    os.rename(p1 / "model.p.off", p1 / "model.p")
+    later = time.time() + 10
+    os.utime(p1 / "pv_active.csv", (later, later))                      # a newer source invalidates the NPZ
+    df = pd.read_csv(p1 / "pv_active.csv"); df.iloc[:, 1] *= 3.0; df.to_csv(p1 / "pv_active.csv", index=False)
+    os.utime(p1 / "pv_active.csv", (later, later))
+    _, prof2 = ingest.load_scenario(str(p1))
+    assert np.allclose(prof2.pv[:, 0], 3.0 * prof0.pv[:, 0])
 
 
 def test_unsupported_content_is_refused():
@@ -118,3 +135,26 @@ def test_unsupported_content_is_refused():
     t["load"].loc[0, "const_z_percent"] = 30.0
     with pytest.raises(NotImplementedError):
         ingest.net_from_tables(t)
+
+
+def test_export_format_round_trips_exactly(tmp_path):
+    """JSON network document + one-file NPZ scenario; bit-exact round trip, picked up by load_scenario."""
+    from mapdn_b200 import cases, ingest
+    net, prof = cases.make_case("case141"), cases.make_profiles("case141", n_days=3)
+    back = ingest.net_from_json(ingest.net_to_json(net))
+    for k in ingest._NET_ARRAYS:
+        a, b = getattr(net, k), getattr(back, k)
+        assert a.dtype == b.dtype and np.array_equal(a, b), k
+    for k in ingest._NET_SCALARS:
+        assert getattr(net, k) == getattr(back, k), k
+    assert back.zone_names == net.zone_names and back.obs_dim == net.obs_dim
+    with pytest.raises(ValueError):
+        ingest.net_from_json('{"format": "something else"}')
+
+    out = ingest.save_scenario_npz(str(tmp_path), net, prof)
+    assert out.endswith("scenario.npz")
+    n2, p2 = ingest.load_scenario(str(tmp_path), pv_scale=0.5, demand_scale=2.0)     # no model.p / CSVs needed
+    assert np.array_equal(n2.br_x, net.br_x) and np.array_equal(n2.sgen_zone, net.sgen_zone)
+    assert np.array_equal(p2.pv, prof.pv * 0.5) and np.array_equal(p2.load_q, prof.load_q * 2.0)
+    assert p2.steps_per_hour == prof.steps_per_hour and p2.n_days == prof.n_days
+    assert np.array_equal(p2.s_max, 1.2 * (prof.pv * 0.5).max(axis=0))
