@@ -93,8 +93,14 @@ def run_reference(args):
     sc = args.scenario
     barrier = cases.SCENARIOS[sc]["barrier"]
     arm = CpuArm(sc, barrier)
-    sample = args.cpu_sample or 8 * arm.cores                 # env-steps per "step" of this arm
-    for _ in range(args.warmup):
+    # env-steps per "step" of this arm: a bounded sample of the 4096-env batch, sized from the rate seen in the first
+    # warm-up pass so that warm-up + K timed steps take about two minutes whatever K is (at least one env-step per core)
+    sample = args.cpu_sample or 2 * arm.cores
+    n0, dt0 = arm.run(sample)
+    if not args.cpu_sample:
+        budget_steps = (n0 / dt0) * 100.0 / max(1, args.steps + args.warmup)
+        sample = int(min(8 * arm.cores, max(arm.cores, budget_steps // arm.cores * arm.cores)))
+    for _ in range(max(0, args.warmup - 1)):
         arm.run(sample)
     done, t = 0, 0.0
     for _ in range(args.steps):
