@@ -344,7 +344,9 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
       double2 s01 = make_double2(0.0, 0.0), s23 = s01, tt = s01;     // Schur update produced by this lane's last step
       for (int st = 0; st < p.n_esteps; ++st) {
         const uint64_t ed_next2 = h.esched[min(st + 2, p.n_esteps - 1) * G + gl];   // independent of the data
+#ifndef MAPDN_EXP_CHILD_LOADS_FIRST
         const Own own_next = load_own(ed_next);          // not touched before its own step
+#endif
         const int i = static_cast<int>(ed & 0xFFFFu);
         const int c0 = static_cast<int>((ed >> 16) & 0xFFFFu), c1 = static_cast<int>((ed >> 32) & 0xFFFFu);
         const unsigned fl = static_cast<unsigned>(ed >> 48);
@@ -356,6 +358,9 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
         double2 p01 = s01, p23 = s23, pt = tt;
         if (fl & kEschedLoad0) { const double2* k0 = s.node(c0); p01 = k0[A_UP]; p23 = k0[A_DN]; pt = k0[A_T]; }
         d01.x -= p01.x; d01.y -= p01.y; d23.x -= p23.x; d23.y -= p23.y; r.x -= pt.x; r.y -= pt.y;
+#ifdef MAPDN_EXP_CHILD_LOADS_FIRST      // experiment: prefetch the next step's blocks behind the child loads
+        const Own own_next = load_own(ed_next);
+#endif
         if (fl & kEschedLoad1) {                          // child 1 (branching buses only): always shared memory
           const double2* k1 = s.node(c1);
           const double2 q01 = k1[A_UP], q23 = k1[A_DN], qt = k1[A_T];
