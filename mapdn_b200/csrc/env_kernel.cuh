@@ -29,11 +29,21 @@ namespace mapdn {
 // Profile builds (MAPDN_PROFILE_BUILD=1 python -m mapdn_b200.build): clock64 totals per phase of warp 0 of block 0,
 // printed by launch_env_kernel (scripts/phase_prof.py). Compiled out otherwise.
 #ifdef MAPDN_PROFILE
-#define PROF_DECL long long _pt = clock64(); long long _acc[12] = {0,0,0,0,0,0,0,0,0,0,0,0};
+#define PROF_DECL long long _pt = clock64(); long long _acc[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0};
 #define PROF(k) { long long _t = clock64(); _acc[k] += _t - _pt; _pt = _t; }
+// inside one forward-sweep step (slots 12..15; they overlap slot 5 "elim"): [12] loop top -> children subtracted (load
+// wait), [13] -> results stored (arithmetic), [14] step executions, [15] linear solves
+#define PROF_STEP_BEGIN long long _s0 = clock64();
+#define PROF_STEP_MID long long _s1 = clock64(); _acc[12] += _s1 - _s0;
+#define PROF_STEP_END { _acc[13] += clock64() - _s1; _acc[14] += 1; }
+#define PROF_COUNT(k) { _acc[k] += 1; }
 #else
 #define PROF_DECL
 #define PROF(k)
+#define PROF_STEP_BEGIN
+#define PROF_STEP_MID
+#define PROF_STEP_END
+#define PROF_COUNT(k)
 #endif
 
 enum Mode { MODE_SOLVE = 0, MODE_STEP = 1, MODE_RESET = 2 };
@@ -343,6 +353,7 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
       Own own = load_own(ed);
       double2 s01 = make_double2(0.0, 0.0), s23 = s01, tt = s01;     // Schur update produced by this lane's last step
       for (int st = 0; st < p.n_esteps; ++st) {
+        PROF_STEP_BEGIN
         const uint64_t ed_next2 = h.esched[min(st + 2, p.n_esteps - 1) * G + gl];   // independent of the data
 #ifndef MAPDN_EXP_CHILD_LOADS_FIRST
         const Own own_next = load_own(ed_next);          // not touched before its own step
@@ -376,6 +387,7 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
             r.x -= xt.x; r.y -= xt.y;
           }
         }
+        PROF_STEP_MID
         // adjugate form: everything that does not need 1/det runs beside the reciprocal (shorter chain, +8 flops)
         const double idet = fast_rcp(d01.x * d23.y - d01.y * d23.x);
         const double ca0 = d23.y * r.x - d01.y * r.y, ca1 = d01.x * r.y - d23.x * r.x;   // adj(D) r
@@ -396,7 +408,9 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
           nd[A_D23] = make_double2(m10, m11);
         }
         ed = ed_next; ed_next = ed_next2; own = own_next;
+        PROF_STEP_END
       }
+      PROF_COUNT(15)
       grp_sync<G>(gidx);                                 // the last step's results are visible to the back sweep
     }
     PROF(5)
@@ -965,7 +979,7 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
     PROF(11)
   }
 #ifdef MAPDN_PROFILE
-  if (p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) for (int k = 0; k < 12; ++k) p.prof[k] = _acc[k];
+  if (p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) for (int k = 0; k < 16; ++k) p.prof[k] = _acc[k];
 #endif
   if (!hot_ready) stage_hot_wait(&stage_bar);   // never exit with the bulk copy still in flight
 }

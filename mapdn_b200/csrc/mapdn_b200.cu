@@ -245,8 +245,8 @@ mapdn_status launch_env_kernel(mapdn_env* e, int mode, Params& p, cudaStream_t s
   grid = (needed + rounds - 1) / rounds;       // balance the persistent loop
 #ifdef MAPDN_PROFILE
   static long long* d_prof = nullptr;
-  if (!d_prof) cudaMalloc(&d_prof, 12 * sizeof(long long));
-  cudaMemset(d_prof, 0, 12 * sizeof(long long));
+  if (!d_prof) cudaMalloc(&d_prof, 16 * sizeof(long long));
+  cudaMemset(d_prof, 0, 16 * sizeof(long long));
   p.prof = d_prof;
 #endif
   p.helper_threads = e->helper_threads;
@@ -255,7 +255,7 @@ mapdn_status launch_env_kernel(mapdn_env* e, int mode, Params& p, cudaStream_t s
   e->launches++;
 #ifdef MAPDN_PROFILE
   {
-    long long hp[12];
+    long long hp[16];
     cudaDeviceSynchronize();
     cudaMemcpy(hp, d_prof, sizeof(hp), cudaMemcpyDeviceToHost);
     static const char* nm[12] = {"-", "setup+prologue", "init/update", "edges", "F/diag", "elim", "backsub", "reload+slack",
@@ -264,6 +264,9 @@ mapdn_status launch_env_kernel(mapdn_env* e, int mode, Params& p, cudaStream_t s
     for (int k = 0; k < 12; ++k) tot += hp[k];
     fprintf(stderr, "[prof mode=%d nb=%d] total %lld cyc:", mode, p.nb, tot);
     for (int k = 1; k < 12; ++k) fprintf(stderr, " %s=%lld", nm[k], hp[k]);
+    if (hp[14] > 0)
+      fprintf(stderr, " | forward-sweep step: %lld executions in %lld solves, load wait %lld + arithmetic %lld cyc per step",
+              hp[14], hp[15], hp[12] / hp[14], hp[13] / hp[14]);
     fprintf(stderr, "\n");
   }
 #endif
