@@ -429,11 +429,16 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
       double2 xl = make_double2(0.0, 0.0);               // dx of the node this lane solved in the previous step
       for (int st = 0; st < p.n_bsteps; ++st) {
         const uint64_t bd_next2 = h.bsched[max(0, min(st + 2, p.n_bsteps - 1)) * G + gl];
+#ifndef MAPDN_EXP_CHILD_LOADS_FIRST
         const OwnB own_next = load_own(bd_next);         // D^-1 J and D^-1 r are final since the forward sweep
+#endif
         double2* nd = s.node(static_cast<int>(bd & 0xFFFFu));
         grp_sync<G>(gidx);                                    // the previous step's dx are visible
         double2 xp = xl;
         if (!((bd >> 32) & 1u)) xp = s.node(static_cast<int>((bd >> 16) & 0xFFFFu))[A_R];
+#ifdef MAPDN_EXP_CHILD_LOADS_FIRST
+        const OwnB own_next = load_own(bd_next);         // experiment: behind the parent's dx the step waits for
+#endif
         double2 x = own.x;
         x.x -= own.m01.x * xp.x + own.m01.y * xp.y;
         x.y -= own.m23.x * xp.x + own.m23.y * xp.y;
