@@ -642,6 +642,70 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
       // ---- helper warp: next profile row of every env of this round (reference _set_demand_and_pv :491-513:
       //      t = self.steps before the increment) + |N(0,1)| * std noise in Box-Muller pairs (2m, 2m+1) over the
       //      elements [pv | load_p | load_q]; new pv goes to the env's scratch (for the obs), loads straight to HBM ----
+#ifdef MAPDN_EXP_HELPER_V2
+      // experiment: software-pipelined rounds. The per-env scalars of round k+2 and the
+      // profile values of round k+1 are in flight while round k's Box-Muller pair is computed; nothing read here is
+      // written by the solvers before barrier 2, so the first loads are issued ahead of barrier 1 (only the stores
+      // to cur_* have to wait for it).
+      {
+        const int n_elem = ng + 2 * nl, n_pair = (n_elem + 1) / 2, n_work = epb * n_pair;
+        const int hl = threadIdx.x - n_solver_threads, T = n_helper_threads;
+        struct HS { int e, m, env, steps; long long nrow; uint32_t ep; bool ok; };
+        struct HR { double v[2], sd[2]; };
+        auto load_scalars = [&](int w) {
+          HS a; a.ok = w < n_work; a.e = 0; a.m = 0; a.env = 0; a.steps = 0; a.nrow = 0; a.ep = 0u;
+          if (a.ok) { a.e = w / n_pair; a.m = w - a.e * n_pair; a.env = base + a.e; a.ok = a.env < p.nb; }
+          if (a.ok) {
+            a.steps = p.steps[a.env];
+            a.nrow = p.start_row[a.env] + a.steps;
+            if (a.nrow > p.n_rows - 1) a.nrow = p.n_rows - 1;
+            a.ep = p.episode[a.env];
+          }
+          return a;
+        };
+        auto load_rows = [&](const HS& a) {
+          HR r; r.v[0] = r.v[1] = r.sd[0] = r.sd[1] = 0.0;
+          if (a.ok) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int el = 2 * a.m + u;
+              if (el >= n_elem) break;
+              if (el < ng) { r.v[u] = __ldg(p.prof_pv + a.nrow * ng + el); r.sd[u] = __ldg(p.pv_std + el); }
+              else if (el < ng + nl) { const int l = el - ng; r.v[u] = __ldg(p.prof_lp + a.nrow * nl + l); r.sd[u] = __ldg(p.lp_std + l); }
+              else { const int l = el - ng - nl; r.v[u] = __ldg(p.prof_lq + a.nrow * nl + l); r.sd[u] = __ldg(p.lq_std + l); }
+            }
+          }
+          return r;
+        };
+        HS s0 = load_scalars(hl), s1 = load_scalars(hl + T);
+        HR r0 = load_rows(s0);
+        named_bar_sync(1, blockDim.x);                 // the solvers have read the current rows
+        for (int w = hl; w < n_work; w += T) {
+          const HS s2 = load_scalars(w + 2 * T);
+          const HR r1 = load_rows(s1);
+          if (s0.ok) {
+            RngKey key_h{k0, k1, static_cast<uint32_t>(p.env_id_offset + s0.env), s0.ep * 8u};
+            double z[2] = {0.0, 0.0};
+            if (p.add_noise) half_normal_pair(key_h, static_cast<uint32_t>(s0.steps), s0.m, z[0], z[1]);
+            double* pv_next = reinterpret_cast<double*>(reinterpret_cast<double2*>(smem_raw + hl_bytes) +
+                                                         static_cast<size_t>(s0.e) * p.env_stride2 + p.scratch_off2);
+            const size_t hL = static_cast<size_t>(s0.env) * nl, hG = static_cast<size_t>(s0.env) * ng;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int el = 2 * s0.m + u;
+              if (el >= n_elem) break;
+              const double val = r0.v[u] + r0.sd[u] * z[u];
+              if (el < ng) { pv_next[el] = val; p.cur_pv[hG + el] = val; }
+              else if (el < ng + nl) p.cur_pl[hL + (el - ng)] = val;
+              else p.cur_ql[hL + (el - ng - nl)] = val;
+            }
+          }
+          s0 = s1; s1 = s2; r0 = r1;
+        }
+      }
+      named_bar_arrive(2, blockDim.x);                 // new pv of every env is in shared memory
+      continue;
+#endif
       named_bar_sync(1, blockDim.x);                   // the solvers have read the current rows
       const int n_elem = ng + 2 * nl, n_pair = (n_elem + 1) / 2;
       const int hl = threadIdx.x - n_solver_threads;
