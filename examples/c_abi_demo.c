@@ -88,7 +88,7 @@ int main(void) {
   uint8_t* term = malloc(BATCH);
   if (!actions || !reward || !info || !obs || !term) return 1;
 
-  if ((st = mapdn_reset(env, NULL, NULL, /*add_noise=*/1, NULL, NULL, NULL)) != MAPDN_OK) return die("mapdn_reset", st);
+  if ((st = mapdn_reset(env, NULL, NULL, /*add_noise=*/1, NULL, NULL, /*converged_dev=*/NULL, NULL)) != MAPDN_OK) return die("mapdn_reset", st);
   for (int k = 0; k < N_STEPS; ++k) {
     for (int e = 0; e < BATCH; ++e)
       for (int g = 0; g < N_SGEN; ++g) actions[e * N_SGEN + g] = -0.8 + 1.6 * ((e * 7 + g * 3 + k) % 11) / 10.0;

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MAPDN_ABI_VERSION 1
+#define MAPDN_ABI_VERSION 2
 #define MAPDN_N_INFO 11   /* info dict keys, reference :585-606,621 (order: mapdn_info_key) */
 
 typedef enum {
@@ -66,7 +66,9 @@ typedef enum {
   MAPDN_FIELD_Q_LOAD = 8,    /* load.q_mvar        [B, n_load]                          */
   MAPDN_FIELD_SUM_REWARDS = 9, /* self.sum_rewards [B]                                  */
   MAPDN_FIELD_STEPS = 10,    /* self.steps as fp64 [B]                                  */
-  MAPDN_FIELD_START_ROW = 11 /* episode window start row as fp64 [B]                    */
+  MAPDN_FIELD_START_ROW = 11,/* episode window start row as fp64 [B]                    */
+  MAPDN_FIELD_NR_ITERS = 12  /* Newton iterations of the last power flow as fp64 [B]    */
+                             /* (max_iter when it diverged; SURVEY 8d side metric)      */
 } mapdn_field;
 
 /*
@@ -165,12 +167,16 @@ mapdn_status mapdn_get_dims(const mapdn_env* env, mapdn_dims* out);
  * reset / manual_reset (reference :96-176). start_dhi_dev: int32 [B,3] = (day, hour, interval)
  * per env (manual_reset semantics) or NULL to sample hour/day/interval on the device
  * (reference :381-398). Envs whose initial power flow diverges are re-drawn on the device
- * (reference retry loop :108-133). mask_dev: uint8 [B] (NULL = all) selects envs to reset.
- * Outputs may be NULL.
+ * (reference retry loop :108-133; the reference retries for ever, the device gives up after 16
+ * draws per call and reports it: converged_dev [B] uint8, 1 = solved, 0 = every draw diverged -
+ * call again with those envs in mask_dev). mask_dev: uint8 [B] (NULL = all) selects envs to
+ * reset; converged_dev is written for the selected envs only. A manual start outside the
+ * profile store is clamped to the last window that fits. Outputs may be NULL.
  */
 mapdn_status mapdn_reset(mapdn_env* env, const int32_t* start_dhi_dev, const uint8_t* mask_dev,
                          int32_t add_noise, double* obs_dev /*[B,n_agents,obs_dim]*/,
-                         double* state_dev /*[B,state_dim]*/, void* stream);
+                         double* state_dev /*[B,state_dim]*/, uint8_t* converged_dev /*[B] or NULL*/,
+                         void* stream);
 
 /*
  * step (reference :178-211): q = a*sqrt(s_max^2 - p_pv^2) -> Newton-Raphson power flow ->
@@ -187,6 +193,21 @@ mapdn_status mapdn_step(mapdn_env* env, const double* actions_dev /*[B,n_sgen]*/
 mapdn_status mapdn_step_host(mapdn_env* env, const double* actions_host, int32_t add_noise,
                              double* reward_host, uint8_t* terminated_host, double* info_host,
                              double* obs_host, void* stream);
+
+/*
+ * Host path without staging copies: every buffer must be page-locked host memory (cudaHostAlloc / cudaHostRegister;
+ * unified addressing). The fused kernel reads the actions from and writes reward / terminated / info / observations
+ * to host memory directly, so the PCIe transfer of the observations overlaps the kernel instead of following it.
+ * obs_is_f32: obs_host is float [B,n_agents,obs_dim] instead of double. skip_padding: the zero padding at the end of
+ * each agent's row (reference :270-274; it never changes) is not rewritten - the caller zero-fills obs_host once.
+ * sync = 0 returns right after the launch (results are valid after mapdn_wait / a stream synchronisation): the
+ * caller's policy for the next step can run while the device works.
+ */
+mapdn_status mapdn_step_host_pinned(mapdn_env* env, const double* actions_host, int32_t add_noise,
+                                    double* reward_host, uint8_t* terminated_host, double* info_host,
+                                    void* obs_host, int32_t obs_is_f32, int32_t skip_padding, int32_t sync,
+                                    void* stream);
+mapdn_status mapdn_wait(mapdn_env* env, void* stream);
 
 /*
  * Variants that deliver the observations in fp32 - what the reference's learners consume (prep_obs casts to
@@ -214,6 +235,19 @@ mapdn_status mapdn_solve(mapdn_env* env, int32_t nb, const double* p_load, const
                          const double* p_sgen, const double* q_sgen, double* vm, double* va_deg,
                          double* p_bus, double* q_bus, double* pl, int32_t* iters,
                          uint8_t* converged, void* stream);
+
+/*
+ * Droop-control baseline of the paper, one control instant per env in ONE launch (reference
+ * traditional_control/pf_droop_matpower_all.m:121-152 loop, :196-231 q(v) characteristic): starting from q = 0, run
+ * the power flow, stop when ||v_pv - v_pv_prev||_2 < tol, else q <- (1 - gain) q + gain q_droop(v_pv); at most max_ite
+ * power flows (script: gain 0.1, tol 1e-4, max_ite 100). Inputs dev fp64: p_load,q_load [nb,n_load], p_sgen [nb,n_sgen],
+ * s_rated, q_max_manual [n_sgen]. Outputs: vm [nb,n_bus] (may be NULL), q_sgen [nb,n_sgen] = the q of the last power
+ * flow, loss [nb] = sum of res_line.pl_mw, iterations int32 [nb] = power flows run. No host synchronisation.
+ */
+mapdn_status mapdn_droop(mapdn_env* env, int32_t nb, const double* p_load, const double* q_load,
+                         const double* p_sgen, const double* s_rated, const double* q_max_manual,
+                         double gain, double tol, int32_t max_ite, double* vm, double* q_sgen,
+                         double* loss, int32_t* iterations, void* stream);
 
 /* Ybus as assembled on the device (dense row-major complex [n_bus,n_bus] -> two host arrays);
  * test hook for the makeYbus restatement. */

@@ -24,7 +24,9 @@ INFO_KEYS = ("percentage_of_v_out_of_control", "percentage_of_lower_than_lower_v
              "average_voltage_deviation", "average_voltage", "max_voltage_drop_deviation",
              "max_voltage_rise_deviation", "total_line_loss", "q_loss", "destroy")
 FIELDS = dict(vm=0, va_deg=1, p_bus=2, q_bus=3, p_sgen=4, q_sgen=5, line_loss=6, p_load=7, q_load=8,
-              sum_rewards=9, steps=10, start_row=11)
+              sum_rewards=9, steps=10, start_row=11, nr_iters=12)
+
+ABI_VERSION = 2
 
 _pd = C.POINTER(C.c_double)
 _pi = C.POINTER(C.c_int32)
@@ -65,8 +67,8 @@ class DimsC(C.Structure):
 
 
 EXPORTS = ("mapdn_abi_version", "mapdn_last_error", "mapdn_create", "mapdn_destroy", "mapdn_get_dims",
-           "mapdn_reset", "mapdn_step", "mapdn_step_host", "mapdn_step_f32obs", "mapdn_step_host_f32obs", "mapdn_get_obs", "mapdn_get_state",
-           "mapdn_get_field", "mapdn_solve", "mapdn_get_ybus_dense", "mapdn_launch_count")
+           "mapdn_reset", "mapdn_step", "mapdn_step_host", "mapdn_step_f32obs", "mapdn_step_host_f32obs", "mapdn_step_host_pinned", "mapdn_wait", "mapdn_get_obs", "mapdn_get_state",
+           "mapdn_get_field", "mapdn_solve", "mapdn_droop", "mapdn_get_ybus_dense", "mapdn_launch_count")
 
 _lib: Optional[C.CDLL] = None
 
@@ -91,15 +93,18 @@ def lib() -> C.CDLL:
                                C.POINTER(vp)]
     L.mapdn_destroy.argtypes = [vp]
     L.mapdn_get_dims.argtypes = [vp, C.POINTER(DimsC)]
-    L.mapdn_reset.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp]
+    L.mapdn_reset.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp, vp]
     L.mapdn_step.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, vp]
     L.mapdn_step_host.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, vp]
     L.mapdn_step_f32obs.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, vp]
     L.mapdn_step_host_f32obs.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, vp]
+    L.mapdn_step_host_pinned.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]
+    L.mapdn_wait.argtypes = [vp, vp]
     L.mapdn_get_obs.argtypes = [vp, vp, vp]
     L.mapdn_get_state.argtypes = [vp, vp, vp]
     L.mapdn_get_field.argtypes = [vp, C.c_int32, vp, vp]
     L.mapdn_solve.argtypes = [vp, C.c_int32] + [vp] * 11 + [vp]
+    L.mapdn_droop.argtypes = [vp, C.c_int32] + [vp] * 5 + [C.c_double, C.c_double, C.c_int32] + [vp] * 5
     L.mapdn_get_ybus_dense.argtypes = [vp, vp, vp]
     L.mapdn_launch_count.argtypes = [vp]
     L.mapdn_launch_count.restype = C.c_int64
@@ -107,7 +112,7 @@ def lib() -> C.CDLL:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("mapdn_abi_version",):
             fn.restype = C.c_int32
-    if L.mapdn_abi_version() != 1:
+    if L.mapdn_abi_version() != ABI_VERSION:
         raise MapdnError("ABI version mismatch between _capi.py and libmapdn_b200.so")
     _lib = L
     return L

@@ -8,15 +8,19 @@ Restates reference ``traditional_control/pf_droop_matpower_all.m`` without MATLA
   collapsed at 1.0, ``q_max = min(sqrt(S_rated^2 - p^2), q_max_manual)``), relaxation ``gain`` 0.1,
   at most 100 power flows per control instant, stop when ||dv_pv||_2 < 1e-4.
 
-Every power flow is one ``mapdn_solve`` launch over the whole batch; envs that have met the stopping
-rule keep their q (the reference breaks out of the loop per instant). OPF (``opf_matpower_all.m``)
-needs an interior-point solver and stays out of scope.
+``droop_control`` is ONE kernel launch per control instant (``mapdn_droop``: the whole relaxed loop, the
+characteristic and the per-env early exit run inside the fused env kernel, no host synchronisation).
+``droop_control_host_loop`` is the round-1 formulation - one ``mapdn_solve`` launch plus a handful of PyTorch
+kernels and a host sync per iteration - kept as the cross-check / timing baseline (``scripts/droop_timing.py``).
+OPF (``opf_matpower_all.m``) needs an interior-point solver and stays out of scope.
 """
 from __future__ import annotations
 
 import torch
 
-__all__ = ["droop_characteristic", "no_control", "droop_control"]
+import ctypes as C
+
+__all__ = ["droop_characteristic", "no_control", "droop_control", "droop_control_host_loop"]
 
 
 def droop_characteristic(p, s_rated, v, q_max_manual, va=0.95, vb=1.0, vc=1.0, vd=1.05):
@@ -45,8 +49,32 @@ def no_control(env, p_load, q_load, p_pv):
 
 
 def droop_control(env, p_load, q_load, p_pv, s_rated, q_max_manual=None, max_ite=100, gain=0.1, tol=1e-4):
-    """Batched droop control. ``p_load/q_load [B, n_load]``, ``p_pv [B, n_sgen]`` CUDA fp64;
-    ``s_rated [n_sgen]`` (= 1.2 * max PV in the reference). Returns dict(vm, q, loss, iterations)."""
+    """Batched droop control, one launch. ``p_load/q_load [B, n_load]``, ``p_pv [B, n_sgen]`` CUDA fp64;
+    ``s_rated [n_sgen]`` (= 1.2 * max PV in the reference). Returns dict(vm, q, loss, iterations) where ``q`` is the
+    reactive power of the last power flow (``result.gen(:,3)`` in the script) and ``iterations`` the number of power
+    flows run per env."""
+    from . import _capi
+    dev = env.device
+    t = lambda x: torch.as_tensor(x, dtype=torch.float64, device=dev).contiguous()
+    p_load, q_load, p_pv, s_rated = t(p_load), t(q_load), t(p_pv), t(s_rated)
+    q_max_manual = s_rated if q_max_manual is None else t(q_max_manual)
+    B, d = int(p_pv.shape[0]), env.dims
+    if tuple(p_load.shape) != (B, d["n_load"]) or tuple(p_pv.shape) != (B, d["n_sgen"]) or s_rated.numel() != d["n_sgen"]:
+        raise ValueError("droop_control: shape mismatch")
+    vm = torch.empty(B, d["n_bus"], dtype=torch.float64, device=dev)
+    q = torch.empty(B, d["n_sgen"], dtype=torch.float64, device=dev)
+    loss = torch.empty(B, dtype=torch.float64, device=dev)
+    iters = torch.empty(B, dtype=torch.int32, device=dev)
+    ptr = lambda x: C.c_void_p(x.data_ptr())
+    _capi.check(env._L.mapdn_droop(env._h, B, ptr(p_load), ptr(q_load), ptr(p_pv), ptr(s_rated), ptr(q_max_manual),
+                                   float(gain), float(tol), int(max_ite), ptr(vm), ptr(q), ptr(loss), ptr(iters),
+                                   env._stream()))
+    return dict(vm=vm, q=q, loss=loss, iterations=iters)
+
+
+def droop_control_host_loop(env, p_load, q_load, p_pv, s_rated, q_max_manual=None, max_ite=100, gain=0.1, tol=1e-4):
+    """The same loop driven from the host: one ``mapdn_solve`` launch + elementwise PyTorch kernels + one host sync per
+    iteration (cross-check of ``droop_control``; envs that met the stopping rule keep their q)."""
     dev = env.device
     p_load = torch.as_tensor(p_load, dtype=torch.float64, device=dev)
     q_load = torch.as_tensor(q_load, dtype=torch.float64, device=dev)

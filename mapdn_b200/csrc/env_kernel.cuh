@@ -46,7 +46,7 @@ namespace mapdn {
 #define PROF_COUNT(k)
 #endif
 
-enum Mode { MODE_SOLVE = 0, MODE_STEP = 1, MODE_RESET = 2 };
+enum Mode { MODE_SOLVE = 0, MODE_STEP = 1, MODE_RESET = 2, MODE_DROOP = 3 };
 constexpr int kMaxResetAttempts = 16;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr double kRad2Deg = 57.295779513082320876798;
@@ -118,16 +118,23 @@ template <int G, int NV> __device__ __forceinline__ void grp_reduce(int gidx, in
   }
 }
 
-// Reciprocal without the library's special-case branch: MUFU.RCP64H seed (~2^-23 rel. error) + two
-// Newton steps (-> ~1 ulp). A zero / denormal pivot yields inf/NaN, which the solver reports as
+// Reciprocal without the library's special-case branch: MUFU.RCP64H seed (~2^-23 rel. error) + one
+// third-order step r (1 + e + e^2), e = 1 - x r (-> ~2^-69 before rounding: 3 dependent FMAs instead of the 4 of
+// two Newton steps). A zero / denormal pivot yields inf/NaN, which the solver reports as
 // "not converged" - the same outcome pandapower reaches through a singular-matrix warning.
 __device__ __forceinline__ double fast_rcp(double x) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#ifdef MAPDN_RCP_TWO_NEWTON
   double e = fma(-x, r, 1.0);
   r = fma(r, e, r);
   e = fma(-x, r, 1.0);
   return fma(r, e, r);
+#else
+  const double e = fma(-x, r, 1.0);
+  const double t = fma(e, e, e);
+  return fma(r, t, r);
+#endif
 }
 
 // sin/cos for the bus angles: distribution-feeder angles are a few degrees, so the common path is a pair of
@@ -234,10 +241,9 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
 
 // Views of the staged static blob and of one env's shared-memory slab.
 struct Hot {
-  const double2 *yup, *ydn, *yii, *ysl;
+  const double2 *yup, *ydn, *yii;
   const uint64_t *ndesc, *esched, *bsched;
-  const uint16_t *lptr, *lidx, *sptr, *sidx, *xptr, *xidx, *node_of_bus, *obs_off, *line_nodes;
-  const double* line_c;
+  const uint16_t *lptr, *lidx, *sptr, *sidx, *xptr, *xidx, *node_of_bus;
   const uint16_t *nbr_ptr, *nbr_idx;   // meshed nets (dense solver) only
   const double2* nbr_y;
 };
@@ -255,6 +261,9 @@ struct Slab {
 // Unknowns (dtheta_i, dV_i/V_i) per PQ bus; J's 2x2 blocks are built from per-edge terms
 //   a_ik = ViVk(G_ik sin t_ik - B_ik cos t_ik),  b_ik = ViVk(G_ik cos t_ik + B_ik sin t_ik)
 // and eliminated leaf-to-root (no fill on a tree), then back-substituted root-to-leaf.
+// Per iteration: ONE pass over the buses (edge terms of (i, parent) + the children's terms recomputed from their
+// voltages + mismatch + diagonal blocks), the forward sweep, and a back sweep that also applies the update
+// (theta += dtheta, V += V dV/V, V = Vm exp(j theta)) to the bus it has just solved.
 // Returns converged; `iters` = number of linear solves (pandapower's iteration count).
 // ------------------------------------------------------------------------------------------
 template <int G>
@@ -265,17 +274,18 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
 ) {
   const int npq = p.npq;
 
-  // flat start (pandapower init="auto"): |V| = vm_init, angle 0 on every PQ bus; sentinel record
+  // flat start (pandapower init="auto"): |V| = vm_init, angle 0 on every PQ bus; sentinel record (slack voltage,
+  // all-zero Jacobian terms: the "no child" / "no parent" slot); trash record (idle lanes: dx = 0 for ever)
   for (int i = gl; i <= npq + 1; i += G) {
     const bool sl = (i == npq);
     double2* nd = s.node(i);
     nd[A_VV] = sl ? make_double2(p.vm0, p.va0) : make_double2(p.vm_init, 0.0);
     nd[A_EF] = sl ? make_double2(p.e0, p.f0) : make_double2(p.vm_init, 0.0);
-    nd[A_UP] = make_double2(0.0, 0.0);      // record npq is the "no child" slot
+    nd[A_UP] = make_double2(0.0, 0.0);
     nd[A_DN] = make_double2(0.0, 0.0);
     nd[A_T] = make_double2(0.0, 0.0);
-    nd[A_R] = make_double2(0.0, 0.0);       // record npq is also the "no parent" slot of the back sweep
-    if (i >= npq) { nd[A_D01] = make_double2(1.0, 0.0); nd[A_D23] = make_double2(0.0, 1.0); }
+    nd[A_R] = make_double2(0.0, 0.0);
+    if (i >= npq) { nd[A_D01] = make_double2(sl ? 1.0 : 0.0, 0.0); nd[A_D23] = make_double2(0.0, sl ? 1.0 : 0.0); }
   }
   grp_sync<G>(gidx);
 
@@ -284,6 +294,54 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
   iters = 0;
   const double2 v0 = make_double2(p.e0, p.f0);
   while (true) {
+#ifdef MAPDN_FUSED_MISMATCH
+    PROF(3)
+    // --- one pass per bus: Jacobian terms of the edge (i, parent) in both directions (kept for the sweeps), the terms of
+    //     the edges to the children (recomputed from the children's voltages: cheaper than a second pass + barrier),
+    //     mismatch F = S_calc - S_spec and the diagonal blocks ---
+    double nrm = 0.0;
+#pragma unroll 2
+    for (int i = gl; i < npq; i += G) {
+      const uint64_t ndc = h.ndesc[i];
+      const int pa = static_cast<int>(ndc & 0xFFFFu);             // roots: sentinel record, Y = 0
+      const int c0 = static_cast<int>((ndc >> 16) & 0xFFFFu), c1 = static_cast<int>((ndc >> 32) & 0xFFFFu);
+      const int nx = static_cast<int>((ndc >> 48) & 0x7FFFu);
+      double2* nd = s.node(i);
+      const double2 vi = nd[A_EF], vp = s.node(pa)[A_EF];
+      const double2 w0 = s.node(c0)[A_EF], w1 = s.node(c1)[A_EF];  // no child: sentinel record, Y = 0
+      const double2 yu = h.yup[i], yd = h.ydn[i];
+      const double2 y0 = h.ydn[c0], y1 = h.ydn[c1];                // Y[i, child]
+      const double2 sp = nd[A_SP];
+      const double2 ys = (ndc >> 63) ? __ldg(p.ysl + i) : make_double2(0.0, 0.0);   // Y[i, slack]: slack-adjacent buses only
+      const double2 yi = h.yii[i];
+      const double cc = vi.x * vp.x + vi.y * vp.y;                 // ViVp cos(ti - tp)
+      const double ss = vi.y * vp.x - vi.x * vp.y;                 // ViVp sin(ti - tp)
+      const double2 u = make_double2(yu.x * ss - yu.y * cc, yu.x * cc + yu.y * ss);      // (a, b) of J[i, parent]
+      const double2 d = make_double2(-yd.x * ss - yd.y * cc, yd.x * cc - yd.y * ss);     // (a, b) of J[parent, i]
+      const double k0c = w0.x * vi.x + w0.y * vi.y, k0s = w0.y * vi.x - w0.x * vi.y;     // child 0 seen from i: t_i - t_c
+      const double k1c = w1.x * vi.x + w1.y * vi.y, k1s = w1.y * vi.x - w1.x * vi.y;
+      const double cs0 = vi.x * v0.x + vi.y * v0.y, sn0 = vi.y * v0.x - vi.x * v0.y;
+      double sa = ys.x * sn0 - ys.y * cs0 + u.x + (-y0.x * k0s - y0.y * k0c) + (-y1.x * k1s - y1.y * k1c);
+      double sb = ys.x * cs0 + ys.y * sn0 + u.y + (y0.x * k0c - y0.y * k0s) + (y1.x * k1c - y1.y * k1s);
+      if (p.has_extra_children) {          // warp-uniform: only nets with a bus of degree > 3
+#pragma unroll 1
+        for (int c = c1 + 1; c <= c1 + nx; ++c) {
+          const double2 w = s.node(c)[A_EF], y = h.ydn[c];
+          const double kc = w.x * vi.x + w.y * vi.y, ks = w.y * vi.x - w.x * vi.y;
+          sa += -y.x * ks - y.y * kc; sb += y.x * kc - y.y * ks;
+        }
+      }
+      const double vv = vi.x * vi.x + vi.y * vi.y;
+      const double gv = yi.x * vv, bv = yi.y * vv;
+      const double P = gv + sb, Q = sa - bv;
+      const double Fp = P - sp.x, Fq = Q - sp.y;
+      nd[A_UP] = u; nd[A_DN] = d;
+      nd[A_D01] = make_double2(-Q - bv, P + gv);     // dP/dtheta, dP/dV * V
+      nd[A_D23] = make_double2(P - gv, Q - bv);      // dQ/dtheta, dQ/dV * V
+      nd[A_R] = make_double2(-Fp, -Fq);
+      nrm = nanmax(nrm, nanmax(fabs(Fp), fabs(Fq)));
+    }
+#else
     PROF(2)
     // --- per-edge terms of (i, parent): row i / col parent and row parent / col i ---
 #pragma unroll 4
@@ -305,12 +363,12 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
     for (int i = gl; i < npq; i += G) {
       const uint64_t ndc = h.ndesc[i];
       const int c0 = static_cast<int>((ndc >> 16) & 0xFFFFu), c1 = static_cast<int>((ndc >> 32) & 0xFFFFu);
-      const int nx = static_cast<int>(ndc >> 48);
+      const int nx = static_cast<int>((ndc >> 48) & 0x7FFFu);
       double2* nd = s.node(i);
       const double2 vi = nd[A_EF];
       const double2 u = nd[A_UP], a0 = s.node(c0)[A_DN], a1 = s.node(c1)[A_DN];  // roots: UP = 0; no child: zero slot
       const double2 sp = nd[A_SP];
-      const double2 ys = h.ysl[i];                       // zero unless the bus is adjacent to the slack
+      const double2 ys = (ndc >> 63) ? __ldg(p.ysl + i) : make_double2(0.0, 0.0);   // Y[i, slack]: slack-adjacent buses only
       const double2 yi = h.yii[i];
       const double cs0 = vi.x * v0.x + vi.y * v0.y, sn0 = vi.y * v0.x - vi.x * v0.y;
       double sa = ys.x * sn0 - ys.y * cs0 + u.x + a0.x + a1.x;
@@ -328,6 +386,7 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
       nd[A_R] = make_double2(-Fp, -Fq);
       nrm = nanmax(nrm, nanmax(fabs(Fp), fabs(Fq)));
     }
+#endif
     {   // ||F||inf < tol for the whole env <=> every thread of the group is below tol (NaN-safe)
       const bool ok = grp_all<G>(gidx, nrm < p.tol);
       if (!done && ok) { done = true; iters = it; }
@@ -340,7 +399,8 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
     //     split when it is wider than the group), one entry per (step, lane). Lanes follow chains of the
     //     forest: when a bus was eliminated by the same lane in the previous step, its Schur update reaches
     //     the parent in registers (no shared-memory round trip on the critical path); the node's own blocks
-    //     are prefetched one step ahead. Idle lanes work on the trash record: no divergent branches. ---
+    //     are prefetched one step ahead, behind the child loads the step waits for. Idle lanes work on the
+    //     trash record: no divergent branches. ---
     {
       struct Own { double2 d01, d23, r, u, d; };
       auto load_own = [&](uint64_t e) {
@@ -355,9 +415,6 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
       for (int st = 0; st < p.n_esteps; ++st) {
         PROF_STEP_BEGIN
         const uint64_t ed_next2 = h.esched[min(st + 2, p.n_esteps - 1) * G + gl];   // independent of the data
-#ifndef MAPDN_EXP_CHILD_LOADS_FIRST
-        const Own own_next = load_own(ed_next);          // not touched before its own step
-#endif
         const int i = static_cast<int>(ed & 0xFFFFu);
         const int c0 = static_cast<int>((ed >> 16) & 0xFFFFu), c1 = static_cast<int>((ed >> 32) & 0xFFFFu);
         const unsigned fl = static_cast<unsigned>(ed >> 48);
@@ -367,11 +424,10 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
         grp_sync<G>(gidx);                                    // the previous step's Schur updates are visible
         // child 0: this lane's registers (chain) or shared memory (a leaf reads the all-zero sentinel record)
         double2 p01 = s01, p23 = s23, pt = tt;
+        if (fl & kEschedLeaf) { p01 = make_double2(0.0, 0.0); p23 = p01; pt = p01; }     // a lane starting a new chain
         if (fl & kEschedLoad0) { const double2* k0 = s.node(c0); p01 = k0[A_UP]; p23 = k0[A_DN]; pt = k0[A_T]; }
         d01.x -= p01.x; d01.y -= p01.y; d23.x -= p23.x; d23.y -= p23.y; r.x -= pt.x; r.y -= pt.y;
-#ifdef MAPDN_EXP_CHILD_LOADS_FIRST      // experiment: prefetch the next step's blocks behind the child loads
-        const Own own_next = load_own(ed_next);
-#endif
+        const Own own_next = load_own(ed_next);          // not touched before its own step (measured: -2.5 % behind the child loads)
         if (fl & kEschedLoad1) {                          // child 1 (branching buses only): always shared memory
           const double2* k1 = s.node(c1);
           const double2 q01 = k1[A_UP], q23 = k1[A_DN], qt = k1[A_T];
@@ -414,6 +470,49 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
       grp_sync<G>(gidx);                                 // the last step's results are visible to the back sweep
     }
     PROF(5)
+#ifdef MAPDN_FUSED_UPDATE
+    // --- back substitution root -> leaves, same flat-schedule form (step 0 = the roots: parent = the all-zero
+    //     sentinel, dx = D^-1 r); a lane that solved the parent in the previous step keeps dx_parent in registers.
+    //     The bus's update (theta += dtheta, V += V * dV/V, V = Vm exp(j theta)) is applied right here, off the
+    //     dependent chain; dx itself is stored only when a child will fetch it from shared memory. ---
+    {
+      struct OwnB { double2 m01, m23, x, vv; };
+      auto load_own = [&](uint64_t e) {
+        const double2* nd = s.node(static_cast<int>(e & 0xFFFFu));
+        OwnB o; o.m01 = nd[A_D01]; o.m23 = nd[A_D23]; o.x = nd[A_R]; o.vv = nd[A_VV];
+        return o;
+      };
+      uint64_t bd = h.bsched[gl];
+      uint64_t bd_next = h.bsched[max(0, min(1, p.n_bsteps - 1)) * G + gl];
+      OwnB own = load_own(bd);
+      double2 xl = make_double2(0.0, 0.0);               // dx of the node this lane solved in the previous step
+      for (int st = 0; st < p.n_bsteps; ++st) {
+        const uint64_t bd_next2 = h.bsched[max(0, min(st + 2, p.n_bsteps - 1)) * G + gl];
+        const unsigned bfl = static_cast<unsigned>(bd >> 32);
+        double2* nd = s.node(static_cast<int>(bd & 0xFFFFu));
+        grp_sync<G>(gidx);                                    // the previous step's dx are visible
+        double2 xp = xl;
+        if (!(bfl & kBschedRegParent)) xp = s.node(static_cast<int>((bd >> 16) & 0xFFFFu))[A_R];
+        const OwnB own_next = load_own(bd_next);         // D^-1 J and D^-1 r are final since the forward sweep
+        double2 x = own.x;
+        x.x -= own.m01.x * xp.x + own.m01.y * xp.y;
+        x.y -= own.m23.x * xp.x + own.m23.y * xp.y;
+        xl = x;
+        const bool live = !(bfl & kBschedIdle);          // idle lanes (trash record) store nothing
+        if (live && (bfl & kBschedStoreX)) nd[A_R] = x;
+        {
+          double2 v = own.vv;
+          v.y += x.x;
+          v.x += v.x * x.y;
+          double sn, cs;
+          sincos_angle(v.y, &sn, &cs);
+          if (live && !done) { nd[A_VV] = v; nd[A_EF] = make_double2(v.x * cs, v.x * sn); }
+        }
+        bd = bd_next; bd_next = bd_next2; own = own_next;
+      }
+      grp_sync<G>(gidx);
+    }
+#else
     // --- back substitution root -> leaves, same flat-schedule form (roots: dx = D^-1 r already); a lane
     //     that solved the parent in the previous step keeps dx_parent in registers ---
     {
@@ -429,27 +528,24 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
       double2 xl = make_double2(0.0, 0.0);               // dx of the node this lane solved in the previous step
       for (int st = 0; st < p.n_bsteps; ++st) {
         const uint64_t bd_next2 = h.bsched[max(0, min(st + 2, p.n_bsteps - 1)) * G + gl];
-#ifndef MAPDN_EXP_CHILD_LOADS_FIRST
-        const OwnB own_next = load_own(bd_next);         // D^-1 J and D^-1 r are final since the forward sweep
-#endif
+        const unsigned bfl = static_cast<unsigned>(bd >> 32);
         double2* nd = s.node(static_cast<int>(bd & 0xFFFFu));
         grp_sync<G>(gidx);                                    // the previous step's dx are visible
         double2 xp = xl;
-        if (!((bd >> 32) & 1u)) xp = s.node(static_cast<int>((bd >> 16) & 0xFFFFu))[A_R];
-#ifdef MAPDN_EXP_CHILD_LOADS_FIRST
-        const OwnB own_next = load_own(bd_next);         // experiment: behind the parent's dx the step waits for
-#endif
+        if (!(bfl & kBschedRegParent)) xp = s.node(static_cast<int>((bd >> 16) & 0xFFFFu))[A_R];
+        const OwnB own_next = load_own(bd_next);         // D^-1 J and D^-1 r are final since the forward sweep
         double2 x = own.x;
         x.x -= own.m01.x * xp.x + own.m01.y * xp.y;
         x.y -= own.m23.x * xp.x + own.m23.y * xp.y;
-        if (!((bd >> 33) & 1u)) nd[A_R] = x;             // idle lanes (trash record) store nothing
+        if (!(bfl & kBschedIdle)) nd[A_R] = x;           // idle lanes (trash record) store nothing
         xl = x;
         bd = bd_next; bd_next = bd_next2; own = own_next;
       }
       grp_sync<G>(gidx);
     }
     PROF(6)
-    // --- update (theta += dtheta, V += V * dV/V) and V = Vm exp(j theta) ---
+    // --- update (theta += dtheta, V += V * dV/V) and V = Vm exp(j theta): a pass of its own - inside the back sweep the
+    //     sin/cos chain would sit in front of the next step of the in-order warp (measured: +200 cycles per step) ---
 #pragma unroll 4
     for (int i = gl; i < npq; i += G) {
       if (!done) {
@@ -465,6 +561,8 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
       }
     }
     grp_sync<G>(gidx);
+#endif
+    PROF(6)
   }
   return done;
 }
@@ -498,7 +596,7 @@ __device__ __forceinline__ bool nr_solve_dense(const Params& p, const Hot& h, co
     double nrm = 0.0;
     for (int i = lane; i < npq; i += 32) {
       const double2 vi = s.node(i)[A_EF];
-      const double2 ys = h.ysl[i], yi = h.yii[i], sp = s.node(i)[A_SP];
+      const double2 ys = __ldg(p.ysl + i), yi = h.yii[i], sp = s.node(i)[A_SP];
       const double cs0 = vi.x * v0.x + vi.y * v0.y, sn0 = vi.y * v0.x - vi.x * v0.y;
       double sa = ys.x * sn0 - ys.y * cs0, sb = ys.x * cs0 + ys.y * sn0;
       double* rp = ws + static_cast<size_t>(2 * i) * ld;
@@ -575,6 +673,18 @@ __device__ __forceinline__ bool nr_solve_dense(const Params& p, const Hot& h, co
   return done;
 }
 
+// Piece-wise linear q(v) of the droop baseline: reference traditional_control/pf_droop_matpower_all.m:196-231
+// (saturation at va = 0.95 / vd = 1.05, dead band collapsed at vb = vc = 1.0, q_max = min(sqrt(S^2 - p^2), q_max_manual))
+__device__ __forceinline__ double droop_q(double pv, double s_rated, double v, double qmm) {
+  const double va = 0.95, vb = 1.0, vc = 1.0, vd = 1.05;
+  const double q_max = fmin(sqrt(s_rated * s_rated - pv * pv), qmm);
+  if (v <= va) return q_max;
+  if (v > vd) return -q_max;
+  if (v >= vb && v <= vc) return 0.0;
+  if (v < vb) return (q_max - 0.0) / (va - vb) * (v - vb);
+  return (0.0 - q_max) / (vc - vd) * (vc - v);
+}
+
 // sgen.q_mvar from an action: reference _clip_reactive_power :568-572
 __device__ __forceinline__ double clip_q(double a, double pv, double smax) {
   return sqrt(smax * smax - pv * pv) * a;
@@ -595,7 +705,6 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
   h.yup = reinterpret_cast<const double2*>(smem_raw + hl.yup);
   h.ydn = reinterpret_cast<const double2*>(smem_raw + hl.ydn);
   h.yii = reinterpret_cast<const double2*>(smem_raw + hl.yii);
-  h.ysl = reinterpret_cast<const double2*>(smem_raw + hl.ysl);
   h.ndesc = reinterpret_cast<const uint64_t*>(smem_raw + hl.ndesc);
   h.esched = reinterpret_cast<const uint64_t*>(smem_raw + hl.esched);
   h.bsched = reinterpret_cast<const uint64_t*>(smem_raw + hl.bsched);
@@ -606,9 +715,6 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
   h.xptr = reinterpret_cast<const uint16_t*>(smem_raw + hl.xptr);
   h.xidx = reinterpret_cast<const uint16_t*>(smem_raw + hl.xidx);
   h.node_of_bus = reinterpret_cast<const uint16_t*>(smem_raw + hl.node_of_bus);
-  h.obs_off = reinterpret_cast<const uint16_t*>(smem_raw + hl.obs_off);
-  h.line_nodes = reinterpret_cast<const uint16_t*>(smem_raw + hl.line_nodes);
-  h.line_c = reinterpret_cast<const double*>(smem_raw + hl.line_c);
   h.nbr_ptr = reinterpret_cast<const uint16_t*>(smem_raw + hl.nbr_ptr);
   h.nbr_idx = reinterpret_cast<const uint16_t*>(smem_raw + hl.nbr_idx);
   h.nbr_y = reinterpret_cast<const double2*>(smem_raw + hl.nbr_y);
@@ -632,109 +738,89 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
     s.q = s.pv + ng;
     s.scratch = reinterpret_cast<double*>(base + p.scratch_off2);
   }
-  double* stage_pl = s.scratch;          // prologue: scaled load p / q
-  double* stage_ql = s.scratch + nl;
-  double* next_row = s.scratch;          // after the prologue: the helper warp's new sgen.p_mw [n_sgen]
+  // scratch: [0, n_sgen) the helper warps' new sgen.p_mw (MODE_STEP) / the previous PV-bus voltages (MODE_DROOP), then the
+  // per-warp partials of the multi-warp group reductions, then - only when they do not fit there - the staged loads.
+  // Staged (scaled) load p / q of the prologue, 2 n_load doubles: they normally live in the Newton fields of the node
+  // records (UP .. R = 12 contiguous doubles per record), which are dead until the flat start overwrites them.
+  double* next_row = s.scratch;
+  double* red_scratch = s.scratch + ng;
+  const bool stage_rec = p.stage_in_records != 0;
+  double* stage_lin = s.scratch + ng + (G > 32 ? 10 * (G / 32) : 0);
+  auto stage = [&](int k) -> double* {
+    return stage_rec ? s.base + (k / 12) * (2 * kNodeArrays2) + 2 * A_UP + (k % 12) : stage_lin + k;
+  };
   const uint32_t k0 = static_cast<uint32_t>(p.seed), k1 = static_cast<uint32_t>(p.seed >> 32);
 
   for (int base = blockIdx.x * epb; base < p.nb; base += gridDim.x * epb) {
     if (is_helper) {
-      // ---- helper warp: next profile row of every env of this round (reference _set_demand_and_pv :491-513:
+      // ---- helper warps: next profile row of every env of this round (reference _set_demand_and_pv :491-513:
       //      t = self.steps before the increment) + |N(0,1)| * std noise in Box-Muller pairs (2m, 2m+1) over the
-      //      elements [pv | load_p | load_q]; new pv goes to the env's scratch (for the obs), loads straight to HBM ----
-#ifdef MAPDN_EXP_HELPER_V2
-      // experiment: software-pipelined rounds. The per-env scalars of round k+2 and the
-      // profile values of round k+1 are in flight while round k's Box-Muller pair is computed; nothing read here is
-      // written by the solvers before barrier 2, so the first loads are issued ahead of barrier 1 (only the stores
-      // to cur_* have to wait for it).
-      {
-        const int n_elem = ng + 2 * nl, n_pair = (n_elem + 1) / 2, n_work = epb * n_pair;
-        const int hl = threadIdx.x - n_solver_threads, T = n_helper_threads;
-        struct HS { int e, m, env, steps; long long nrow; uint32_t ep; bool ok; };
-        struct HR { double v[2], sd[2]; };
-        auto load_scalars = [&](int w) {
-          HS a; a.ok = w < n_work; a.e = 0; a.m = 0; a.env = 0; a.steps = 0; a.nrow = 0; a.ep = 0u;
-          if (a.ok) { a.e = w / n_pair; a.m = w - a.e * n_pair; a.env = base + a.e; a.ok = a.env < p.nb; }
-          if (a.ok) {
-            a.steps = p.steps[a.env];
-            a.nrow = p.start_row[a.env] + a.steps;
-            if (a.nrow > p.n_rows - 1) a.nrow = p.n_rows - 1;
-            a.ep = p.episode[a.env];
-          }
-          return a;
-        };
-        auto load_rows = [&](const HS& a) {
-          HR r; r.v[0] = r.v[1] = r.sd[0] = r.sd[1] = 0.0;
-          if (a.ok) {
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int el = 2 * a.m + u;
-              if (el >= n_elem) break;
-              if (el < ng) { r.v[u] = __ldg(p.prof_pv + a.nrow * ng + el); r.sd[u] = __ldg(p.pv_std + el); }
-              else if (el < ng + nl) { const int l = el - ng; r.v[u] = __ldg(p.prof_lp + a.nrow * nl + l); r.sd[u] = __ldg(p.lp_std + l); }
-              else { const int l = el - ng - nl; r.v[u] = __ldg(p.prof_lq + a.nrow * nl + l); r.sd[u] = __ldg(p.lq_std + l); }
-            }
-          }
-          return r;
-        };
-        HS s0 = load_scalars(hl), s1 = load_scalars(hl + T);
-        HR r0 = load_rows(s0);
-        named_bar_sync(1, blockDim.x);                 // the solvers have read the current rows
-        for (int w = hl; w < n_work; w += T) {
-          const HS s2 = load_scalars(w + 2 * T);
-          const HR r1 = load_rows(s1);
-          if (s0.ok) {
-            RngKey key_h{k0, k1, static_cast<uint32_t>(p.env_id_offset + s0.env), s0.ep * 8u};
-            double z[2] = {0.0, 0.0};
-            if (p.add_noise) half_normal_pair(key_h, static_cast<uint32_t>(s0.steps), s0.m, z[0], z[1]);
-            double* pv_next = reinterpret_cast<double*>(reinterpret_cast<double2*>(smem_raw + hl_bytes) +
-                                                         static_cast<size_t>(s0.e) * p.env_stride2 + p.scratch_off2);
-            const size_t hL = static_cast<size_t>(s0.env) * nl, hG = static_cast<size_t>(s0.env) * ng;
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int el = 2 * s0.m + u;
-              if (el >= n_elem) break;
-              const double val = r0.v[u] + r0.sd[u] * z[u];
-              if (el < ng) { pv_next[el] = val; p.cur_pv[hG + el] = val; }
-              else if (el < ng + nl) p.cur_pl[hL + (el - ng)] = val;
-              else p.cur_ql[hL + (el - ng - nl)] = val;
-            }
-          }
-          s0 = s1; s1 = s2; r0 = r1;
+      //      elements [pv | load_p | load_q]; new pv goes to the env's scratch (for the obs), loads straight to HBM.
+      //      Two dependent global round trips in total: (A) the per-env scalars of the whole round -> shared memory,
+      //      (B) the profile values, four work items per thread in flight, addresses selected without branches. ----
+      const int n_elem = ng + 2 * nl, n_pair = (n_elem + 1) / 2, n_work = epb * n_pair;
+      const int ht = threadIdx.x - n_solver_threads, T = n_helper_threads;
+      int4* hs = reinterpret_cast<int4*>(smem_raw + p.helper_off);     // per env: (row lo, row hi, steps, episode)
+      asm volatile("bar.sync 15, %0;" ::"r"(T) : "memory");     // helper threads only: the previous round's reads of hs are done
+      for (int e = ht; e < epb; e += T) {
+        const int env_h = base + e;
+        int4 v = make_int4(0, 0, 0, 0);
+        if (env_h < p.nb) {
+          const int steps_h = p.steps[env_h];
+          long long nrow = p.start_row[env_h] + steps_h;
+          if (nrow > p.n_rows - 1) nrow = p.n_rows - 1;
+          v = make_int4(static_cast<int>(nrow & 0xFFFFFFFFll), static_cast<int>(nrow >> 32), steps_h,
+                        static_cast<int>(p.episode[env_h]));
         }
+        hs[e] = v;
       }
-      named_bar_arrive(2, blockDim.x);                 // new pv of every env is in shared memory
-      continue;
-#endif
+      asm volatile("bar.sync 15, %0;" ::"r"(T) : "memory");     // helper threads only
       named_bar_sync(1, blockDim.x);                   // the solvers have read the current rows
-      const int n_elem = ng + 2 * nl, n_pair = (n_elem + 1) / 2;
-      const int hl = threadIdx.x - n_solver_threads;
-      for (int w = hl; w < epb * n_pair; w += n_helper_threads) {
-        const int e = w / n_pair, m = w - e * n_pair, env_h = base + e;
-        if (env_h >= p.nb) continue;
-        const int steps_h = p.steps[env_h];
-        long long nrow = p.start_row[env_h] + steps_h;
-        if (nrow > p.n_rows - 1) nrow = p.n_rows - 1;
-        RngKey key_h{k0, k1, static_cast<uint32_t>(p.env_id_offset + env_h), p.episode[env_h] * 8u};
-        double z[2] = {0.0, 0.0};
-        if (p.add_noise) half_normal_pair(key_h, static_cast<uint32_t>(steps_h), m, z[0], z[1]);
-        double* pv_next = reinterpret_cast<double*>(reinterpret_cast<double2*>(smem_raw + hl_bytes) +
-                                                     static_cast<size_t>(e) * p.env_stride2 + p.scratch_off2);
-        const size_t hL = static_cast<size_t>(env_h) * nl, hG = static_cast<size_t>(env_h) * ng;
+      constexpr int U = 4;
+      for (int w0 = ht; w0 < n_work; w0 += U * T) {
+        double val[U][2], sd[U][2];
+        int e_[U], m_[U];
+        bool ok[U];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int el = 2 * m + u;
-          if (el >= n_elem) break;
-          if (el < ng) {
-            const double pv = __ldg(p.prof_pv + nrow * ng + el) + __ldg(p.pv_std + el) * z[u];
-            pv_next[el] = pv;
-            p.cur_pv[hG + el] = pv;
-          } else if (el < ng + nl) {
-            const int l = el - ng;
-            p.cur_pl[hL + l] = __ldg(p.prof_lp + nrow * nl + l) + __ldg(p.lp_std + l) * z[u];
-          } else {
-            const int l = el - ng - nl;
-            p.cur_ql[hL + l] = __ldg(p.prof_lq + nrow * nl + l) + __ldg(p.lq_std + l) * z[u];
+        for (int u = 0; u < U; ++u) {
+          const int w = w0 + u * T;
+          ok[u] = w < n_work;
+          const int e = ok[u] ? w / n_pair : 0;
+          e_[u] = e; m_[u] = w - e * n_pair;
+          ok[u] = ok[u] && (base + e < p.nb);
+          const int4 sc = hs[e];
+          const long long nrow = (static_cast<long long>(sc.y) << 32) | static_cast<unsigned>(sc.x);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int el = min(2 * m_[u] + k, n_elem - 1);          // an odd n_elem re-reads the last element (not stored)
+            const bool is_pv = el < ng, is_lp = el < ng + nl;
+            const int j = is_pv ? el : (is_lp ? el - ng : el - ng - nl);
+            const double* src = is_pv ? p.prof_pv + nrow * ng : (is_lp ? p.prof_lp + nrow * nl : p.prof_lq + nrow * nl);
+            const double* sds = is_pv ? p.pv_std : (is_lp ? p.lp_std : p.lq_std);
+            val[u][k] = ok[u] ? __ldg(src + j) : 0.0;
+            sd[u][k] = ok[u] ? __ldg(sds + j) : 0.0;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (!ok[u]) continue;
+          const int e = e_[u], m = m_[u], env_h = base + e;
+          const int4 sc = hs[e];
+          RngKey key_h{k0, k1, static_cast<uint32_t>(p.env_id_offset + env_h), static_cast<uint32_t>(sc.w) * 8u};
+          double z[2] = {0.0, 0.0};
+          if (p.add_noise) half_normal_pair(key_h, static_cast<uint32_t>(sc.z), m, z[0], z[1]);
+          double* pv_next = reinterpret_cast<double*>(reinterpret_cast<double2*>(smem_raw + hl_bytes) +
+                                                       static_cast<size_t>(e) * p.env_stride2 + p.scratch_off2);
+          const size_t hL = static_cast<size_t>(env_h) * nl, hG = static_cast<size_t>(env_h) * ng;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int el = 2 * m + k;
+            if (el >= n_elem) break;
+            const double v = val[u][k] + sd[u][k] * z[k];
+            const bool is_pv = el < ng, is_lp = el < ng + nl;
+            double* dst = is_pv ? p.cur_pv + hG + el : (is_lp ? p.cur_pl + hL + (el - ng) : p.cur_ql + hL + (el - ng - nl));
+            *dst = v;
+            if (is_pv) pv_next[el] = v;
           }
         }
       }
@@ -762,7 +848,11 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
     int iters = 0;
     int attempt = 0;
     bool solved = false;
-    for (int round = 0; round < (MODE == MODE_RESET ? kMaxResetAttempts : 1); ++round) {
+    bool dr_active = valid;      // MODE_DROOP: this env has not met the stopping rule yet
+    int dr_iters = 0;
+    double* v_last = s.scratch;                    // MODE_DROOP: PV-bus voltages of the previous power flow [n_sgen]
+    const int n_rounds = (MODE == MODE_RESET) ? kMaxResetAttempts : (MODE == MODE_DROOP ? p.droop_max_ite : 1);
+    for (int round = 0; round < n_rounds; ++round) {
       // ---------------- prologue: element values -> sgen p/q and bus injections ----------------
       if (MODE == MODE_RESET) {
         int day, hour, interval;
@@ -776,16 +866,21 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
         }
         start = interval + static_cast<long long>(hour) * p.steps_per_hour +
                 static_cast<long long>(day) * 24 * p.steps_per_hour;          // :445
+        // a manual start outside the store is clamped to the last window that fits (the host shims validate and
+        // raise; the kernel only guarantees in-bounds reads)
+        start = max(0ll, min(start, p.n_rows - 1 - p.episode_limit));
       }
       long long row = 0;
       if (MODE == MODE_RESET) { row = start + 1; if (row > p.n_rows - 1) row = p.n_rows - 1; }   // t = steps = 1
       const uint32_t c1 = kResetFlag | static_cast<uint32_t>(attempt);
       // (1) coalesced, independent loads of the env's element values into shared memory
+      if (MODE != MODE_DROOP || round == 0) {          // droop: later rounds only change q (in shared memory)
 #pragma unroll 4
       for (int j = gl; j < ng; j += G) {
         double pv, q;
-        if (MODE == MODE_SOLVE) {
-          pv = p.in_pv[eG + j]; q = p.in_q[eG + j];
+        if (MODE == MODE_SOLVE || MODE == MODE_DROOP) {
+          pv = p.in_pv[eG + j]; q = (MODE == MODE_SOLVE) ? p.in_q[eG + j] : 0.0;     // droop starts from q = 0 (:107)
+          if (MODE == MODE_DROOP) v_last[j] = 100.0;                                    // :123
         } else if (MODE == MODE_STEP) {
           pv = p.cur_pv[eG + j];
           q = clip_q(p.actions[eG + j], pv, __ldg(p.s_max + j));             // :553
@@ -802,10 +897,12 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
         }
         s.pv[j] = pv; s.q[j] = q;
       }
+      }
+      // (droop re-stages the loads every round: the staging area is overwritten by the Newton iteration)
 #pragma unroll 4
       for (int l = gl; l < nl; l += G) {
         double pl, ql;
-        if (MODE == MODE_SOLVE) { pl = p.in_pl[eL + l]; ql = p.in_ql[eL + l]; }
+        if (MODE == MODE_SOLVE || MODE == MODE_DROOP) { pl = p.in_pl[eL + l]; ql = p.in_ql[eL + l]; }
         else if (MODE == MODE_STEP) { pl = p.cur_pl[eL + l]; ql = p.cur_ql[eL + l]; }
         else {
           pl = __ldg(p.prof_lp + row * nl + l);
@@ -817,7 +914,7 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
           if (valid) { p.cur_pl[eL + l] = pl; p.cur_ql[eL + l] = ql; }
         }
         const double sc = __ldg(p.lscale + l);
-        stage_pl[l] = pl * sc; stage_ql[l] = ql * sc;
+        *stage(l) = pl * sc; *stage(nl + l) = ql * sc;
       }
       if (!hot_ready) { stage_hot_wait(&stage_bar); hot_ready = true; }
       grp_sync<G>(gidx);
@@ -825,7 +922,7 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
       for (int i = gl; i < npq; i += G) {
         double pd = 0.0, qd = 0.0;
 #pragma unroll 1
-        for (int t = h.lptr[i], te = h.lptr[i + 1]; t < te; ++t) { const int l = h.lidx[t]; pd += stage_pl[l]; qd += stage_ql[l]; }
+        for (int t = h.lptr[i], te = h.lptr[i + 1]; t < te; ++t) { const int l = h.lidx[t]; pd += *stage(l); qd += *stage(nl + l); }
 #pragma unroll 1
         for (int t = h.sptr[i], te = h.sptr[i + 1]; t < te; ++t) {
           const int g = h.sidx[t];
@@ -850,6 +947,32 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
 #endif
       }
       PROF(4)
+      if (MODE == MODE_DROOP) {
+        // relaxed fixed-point loop of pf_droop_matpower_all.m:121-152: stop when ||v_pv - v_pv_last||_2 < tol, else
+        // q <- (1 - gain) q + gain q_droop(v). An env that has stopped keeps its q, so the power flows it still runs
+        // alongside the others of its warp reproduce its final state; the last allowed round does not move q either
+        // (the script reports the q of the last power flow).
+        double part[1] = {0.0};
+        const bool no_max[1] = {false};
+        for (int j = gl; j < ng; j += G) {
+          const double dv = v_last[j] - s.node(__ldg(p.sgen_node + j))[A_VV].x;
+          part[0] += dv * dv;
+        }
+        grp_reduce<G, 1>(gidx, gl, part, no_max, red_scratch);
+        const bool stop = sqrt(part[0]) < p.droop_tol;
+        if (dr_active) { dr_iters = round + 1; if (stop) dr_active = false; }
+        if (grp_exit<G>(!dr_active) || round == n_rounds - 1) break;
+        if (dr_active) {
+          for (int j = gl; j < ng; j += G) {
+            const double v = s.node(__ldg(p.sgen_node + j))[A_VV].x;
+            v_last[j] = v;
+            const double q_new = droop_q(s.pv[j], __ldg(p.droop_s + j), v, __ldg(p.droop_qmm + j));
+            s.q[j] = (1.0 - p.droop_gain) * s.q[j] + p.droop_gain * q_new;
+          }
+        }
+        grp_sync<G>(gidx);
+        continue;
+      }
       if (MODE != MODE_RESET) break;
       if (conv) solved = true;
       if (grp_exit<G>(solved)) break;
@@ -872,7 +995,11 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
       }
     }
     grp_sync<G>(gidx);
-    const bool write_res = valid && (MODE != MODE_STEP || conv);
+    // a reset whose kMaxResetAttempts draws all diverged keeps the env's previous state and reports it (reset_ok)
+    constexpr bool kExplicit = (MODE == MODE_SOLVE || MODE == MODE_DROOP);     // explicit inputs / outputs, no env state
+    const bool write_res = valid && (kExplicit || conv);
+    if (MODE == MODE_RESET && valid && gl == 0 && p.reset_ok != nullptr) p.reset_ok[env] = conv ? 1 : 0;
+    if (!kExplicit && valid && gl == 0) p.nr_iters[env] = conv ? iters : p.max_iter;
 
     // slack injection (pfsoln): S0 = V0 conj(Ybus[0,:] V) -> sentinel record's SP
     {
@@ -913,7 +1040,12 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
     for (int i = gl; i <= npq; i += G) {
       double2* nd = s.node(i);
       const double2 sp = nd[A_SP];
-      const double2 bp = make_double2(-sp.x * p.base_mva, -sp.y * p.base_mva);
+      double2 bp = make_double2(-sp.x * p.base_mva, -sp.y * p.base_mva);
+      if (p.has_shunt) {                   // warp-uniform; pandapower adds the bus shunts' p/q (x vm^2) to res_bus
+        const double2 ef = nd[A_EF];
+        const double v2 = ef.x * ef.x + ef.y * ef.y;
+        bp.x += __ldg(p.sh_g + i) * v2; bp.y -= __ldg(p.sh_b + i) * v2;
+      }
       double2 op = bp;
 #pragma unroll 1
       for (int t = h.xptr[i], te = h.xptr[i + 1]; t < te; ++t) { const int g = h.xidx[t]; op.x += s.pv[g]; op.y += s.q[g]; }
@@ -928,7 +1060,7 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
       const double2* nd = s.node(h.node_of_bus[b]);
       const double2 vv = nd[A_VV], bp = nd[A_BP];
       const double v = vv.x, th = vv.y;
-      if (MODE == MODE_SOLVE) {
+      if (kExplicit) {
         if (valid) {
           if (p.out_vm) p.out_vm[eN + b] = v;
           if (p.out_va) p.out_va[eN + b] = th * kRad2Deg;
@@ -956,19 +1088,30 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
       const size_t ePL = static_cast<size_t>(env) * p.n_line;
 #pragma unroll 4
       for (int k = gl; k < p.n_line; k += G) {
-        const double2 vf = s.node(h.line_nodes[2 * k])[A_EF], vt = s.node(h.line_nodes[2 * k + 1])[A_EF];
+        const ushort2 ft = __ldg(reinterpret_cast<const ushort2*>(p.line_nodes) + k);     // cold tables: once per env-step, coalesced
+        const double2 vf = s.node(ft.x)[A_EF], vt = s.node(ft.y)[A_EF];
         const double cc = vf.x * vt.x + vf.y * vt.y, ss = vf.y * vt.x - vf.x * vt.y;
-        const double* c = h.line_c + 4 * k;
-        const double pl = c[0] * (vf.x * vf.x + vf.y * vf.y) + c[1] * (vt.x * vt.x + vt.y * vt.y) + c[2] * cc + c[3] * ss;
+        const double2 c01 = __ldg(reinterpret_cast<const double2*>(p.line_c) + 2 * k);
+        const double2 c23 = __ldg(reinterpret_cast<const double2*>(p.line_c) + 2 * k + 1);
+        const double pl = c01.x * (vf.x * vf.x + vf.y * vf.y) + c01.y * (vt.x * vt.x + vt.y * vt.y) + c23.x * cc + c23.y * ss;
         sum_pl += pl;
-        if (MODE == MODE_SOLVE) { if (valid && p.out_pl) p.out_pl[ePL + k] = pl; }
+        if (kExplicit) { if (valid && p.out_pl) p.out_pl[ePL + k] = pl; }
         else if (write_res) p.res_pl[ePL + k] = pl;
       }
     }
     PROF(9)
-    if (MODE == MODE_SOLVE) {
+    if (kExplicit) {
+      if (MODE == MODE_DROOP) {
+        double tot[1] = {sum_pl};
+        const bool no_max[1] = {false};
+        grp_reduce<G, 1>(gidx, gl, tot, no_max, red_scratch);
+        if (valid) {
+          for (int j = gl; j < ng; j += G) p.droop_q_out[eG + j] = s.q[j];
+          if (gl == 0) { p.droop_loss_out[env] = tot[0]; p.out_iters[env] = dr_iters; }
+        }
+      }
       if (valid && gl == 0) {
-        if (p.out_iters) p.out_iters[env] = conv ? iters : p.max_iter;
+        if (MODE == MODE_SOLVE && p.out_iters) p.out_iters[env] = conv ? iters : p.max_iter;
         if (p.out_conv) p.out_conv[env] = conv ? 1 : 0;
       }
       grp_sync<G>(gidx);
@@ -979,7 +1122,7 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
       {
         double rv[10] = {cnt_lo, cnt_hi, sum_dev, sum_v, sum_bar, max_drop, max_rise, sum_pl, sum_q_eff, sum_q_try};
         const bool rmax[10] = {false, false, false, false, false, true, true, false, false, false};
-        grp_reduce<G, 10>(gidx, gl, rv, rmax, s.scratch);
+        grp_reduce<G, 10>(gidx, gl, rv, rmax, red_scratch);
         cnt_lo = rv[0]; cnt_hi = rv[1]; sum_dev = rv[2]; sum_v = rv[3]; sum_bar = rv[4];
         max_drop = rv[5]; max_rise = rv[6]; sum_pl = rv[7]; sum_q_eff = rv[8]; sum_q_try = rv[9];
       }
@@ -1021,12 +1164,18 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
       double* o = p.obs + static_cast<size_t>(env) * ng * p.obs_dim;
       const int tot = ng * p.obs_dim;
 #pragma unroll 4
-      for (int idx = gl; idx < tot; idx += G) o[idx] = s.base[h.obs_off[idx]];
+      for (int idx = gl; idx < tot; idx += G) {
+        const int off = __ldg(p.obs_off + idx);
+        if (off != p.obs_skip_off) o[idx] = s.base[off];      // obs_skip_off = the zero slot when the padding is not rewritten
+      }
     } else if (MODE == MODE_STEP && p.obs32 != nullptr && valid) {
       float* o = p.obs32 + static_cast<size_t>(env) * ng * p.obs_dim;
       const int tot = ng * p.obs_dim;
 #pragma unroll 4
-      for (int idx = gl; idx < tot; idx += G) o[idx] = static_cast<float>(s.base[h.obs_off[idx]]);
+      for (int idx = gl; idx < tot; idx += G) {
+        const int off = __ldg(p.obs_off + idx);
+        if (off != p.obs_skip_off) o[idx] = static_cast<float>(s.base[off]);
+      }
     }
     if (MODE == MODE_RESET && p.state != nullptr) {
       // get_state (:213-230): [P_bus | Q_bus | pv | q | vm | va(deg)] restricted to state_space (cold program)

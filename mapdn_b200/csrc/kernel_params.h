@@ -31,22 +31,25 @@ constexpr unsigned kEschedReg0 = 0x100u;    // registers of the same lane (it el
 constexpr unsigned kEschedLoad0 = 0x200u;   // shared memory
 constexpr unsigned kEschedLoad1 = 0x400u;   // child 1 exists (always from shared memory)
 constexpr unsigned kEschedIdle = 0x1000u;   // idle lane of this step: reads the trash record, stores nothing
+constexpr unsigned kEschedLeaf = 0x2000u;   // no child at all: the update is zero (no shared-memory access on the step's chain)
 constexpr unsigned kEschedStore = 0x800u;   // the parent will read this bus's Schur update from shared memory
+// bsched flags (bits 32.. of an entry)
+constexpr unsigned kBschedRegParent = 0x1u; // dx of the parent is in this lane's registers (it solved the parent in the previous step)
+constexpr unsigned kBschedIdle = 0x2u;      // idle lane of this step (trash record)
+constexpr unsigned kBschedStoreX = 0x4u;    // a child will fetch this bus's dx from shared memory
 
 struct HotLayout {        // byte offsets inside the hot static blob (staged into smem per CTA)
-  int yup, ydn;           // double2 [npq]: Y[i,parent], Y[parent,i]   (G, B)
-  int yii, ysl;           // double2 [npq]: Y[i,i], Y[i,slack]
+  int yup, ydn;           // double2 [npq], [npq + 1]: Y[i,parent], Y[parent,i]   (G, B); ydn[npq] = 0 ("no child")
+  int yii;                // double2 [npq]: Y[i,i]
   int ndesc;              // uint64 [npq]: node descriptor, see below
   int esched;             // uint64 [n_esteps * G]: elimination schedule, one entry per (step, lane):
                           //   node | child0<<16 | child1<<32 | flags<<48   (idle lane: trash record)
-  int bsched;             // uint64 [n_bsteps * G]: back-substitution schedule: node | parent<<16 | reg_parent<<32 | idle<<33
+  int bsched;             // uint64 [n_bsteps * G]: back-substitution schedule: node | parent<<16 | kBsched* flags<<32
+                          //   (step 0 = the roots, parent = the all-zero sentinel record)
   int lptr, lidx;         // uint16 [npq+2], [n_load]: node -> loads (CSR); node npq = slack bus
   int sptr, sidx;         // uint16 [npq+2], [n_sgen]: node -> sgens
   int xptr, xidx;         // uint16 [npq+2], [<=n_sgen]: node -> sgens of the node's own zone (obs add-back)
   int node_of_bus;        // uint16 [n_bus]: bus -> node (slack -> npq)
-  int obs_off;            // uint16 [n_sgen*obs_dim]: obs entry -> double offset inside the env slab
-  int line_nodes;         // uint16 [2*n_line]: from / to node of every line (npq = slack)
-  int line_c;             // double [4*n_line]: loss coefficients (see mapdn_b200.cu)
   int nbr_ptr, nbr_idx;   // meshed nets only: uint16 CSR of the PQ-PQ Ybus pattern ([npq+1], [nnz])
   int nbr_y;              // meshed nets only: double2 [nnz]: Y[i,j] (G, B) of each CSR entry
   int bytes;              // total, multiple of 16
@@ -56,7 +59,8 @@ struct HotLayout {        // byte offsets inside the hot static blob (staged int
 //   bits  0-15 parent (the sentinel record npq for roots: zero admittance)
 //   bits 16-31 first child  (npq = none -> zero slot)
 //   bits 32-47 second child (npq = none)
-//   bits 48-63 number of children beyond two (they follow child1 contiguously)
+//   bits 48-62 number of children beyond two (they follow child1 contiguously)
+//   bit  63    the bus is adjacent to the slack bus (Y[i,slack] in the cold table ysl)
 struct Params {
   // ---- sizes ----
   int n_bus, npq, n_load, n_sgen, n_line, n_lev, obs_dim, state_dim, n_slack_adj, slack_bus;
@@ -66,12 +70,22 @@ struct Params {
   int env_stride2;        // double2 elements of smem per env
   int pvq_off2;           // double2 offset of the sgen (pv | q) block inside the env slab
   int scratch_off2;       // double2 offset of the scratch region (prologue staging / next-row prefetch)
+  int stage_in_records;   // the prologue stages the scaled loads in the (dead) Newton fields of the node records
+  int helper_off;         // byte offset (in the CTA's dynamic smem) of the helper warps' per-env scalars: int4 [envs per CTA]
+  int has_shunt;          // any bus shunt: res_bus p/q get the shunt power (cold tables sh_g / sh_b)
   HotLayout hot_layout;
   const unsigned char* hot;
   // ---- cold static (global, read through the read-only path) ----
   const int* bus_of_node;                                     // [npq]
   const double* lscale; const double* sscale;                 // scaling by load id / sgen id
   const int* sl_node; const double* sl_y;                     // slack-adjacent nodes, Y[slack,i] (G,B)
+  // cold tables read once per env-step (coalesced, read-only path) - kept out of the shared-memory blob
+  const double2* ysl;                                         // [npq] Y[i,slack] (zero unless adjacent to the slack)
+  const uint16_t* obs_off;                                    // [n_sgen*obs_dim] obs entry -> double offset in the env slab
+  const uint16_t* line_nodes;                                 // [2*n_line] from / to node of every line (npq = slack)
+  const double* line_c;                                       // [4*n_line] loss coefficients (see mapdn_b200.cu)
+  const int* sgen_node;                                       // [n_sgen] node of each sgen's bus (slack -> npq)
+  const double* sh_g; const double* sh_b;                     // [npq + 1] bus shunt GS / BS (MW / MVAr at 1 p.u.) by node
   const unsigned* obs_src; const int* obs_xptr; const int* obs_xidx;   // cold obs program of get_obs_kernel
   const unsigned* state_src;                                  // state program: kind | bus / sgen index
   const double* s_max; const double* pv_std; const double* lp_std; const double* lq_std;
@@ -88,14 +102,21 @@ struct Params {
   double* cur_pl; double* cur_ql; double* cur_pv; double* cur_q;
   double* res_vm; double* res_va; double* res_p; double* res_q; double* res_pl;
   int* steps; double* sum_rewards; long long* start_row; unsigned* episode;
+  int* nr_iters;          // Newton iterations of the env's last power flow (max_iter when it diverged)
   // ---- launch io ----
   const double* in_pl; const double* in_ql; const double* in_pv; const double* in_q;  // SOLVE
   const double* actions;                                                             // STEP
   const int* start_dhi; const unsigned char* mask; int add_noise;                    // RESET
+  unsigned char* reset_ok;                                                           // RESET: [B] 1 = the env's power flow converged
   double* out_vm; double* out_va; double* out_p; double* out_q; double* out_pl;
   int* out_iters; unsigned char* out_conv;
+  // DROOP (traditional_control/pf_droop_matpower_all.m): rated S and manual q limit per sgen, relaxation, outputs
+  const double* droop_s; const double* droop_qmm; double droop_gain, droop_tol; int droop_max_ite;
+  double* droop_q_out; double* droop_loss_out;
   double* reward; unsigned char* term; double* info; double* obs; double* state;
   float* obs32;           // alternative fp32 destination of the observations (MODE_STEP)
+  int obs_skip_off;       // slab offset whose obs entries are NOT stored: -1 (store everything) or the zero slot (host
+                          // path into a buffer whose padding is already zero: a third fewer bytes over PCIe)
   double* dense_ws;       // meshed nets only: per resident env group, (2 npq) x (2 npq + 1) doubles [J | rhs]
   int dense_stride;       // doubles per group in dense_ws
   long long* prof;        // MAPDN_PROFILE builds: per-phase clock64 totals of warp 0 of block 0

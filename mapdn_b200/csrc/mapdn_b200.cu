@@ -61,7 +61,8 @@ __global__ void ybus_branch_kernel(int n_br, const double* __restrict__ r, const
   if (k >= n_br) return;
   const double st = status[k] ? 1.0 : 0.0;
   const double den = r[k] * r[k] + x[k] * x[k];
-  const double ys_g = st * r[k] / den, ys_b = -st * x[k] / den;          // Ys = stat / (r + jx)
+  // Ys = stat / (r + jx); an out-of-service branch contributes exactly zero (also when r = x = 0)
+  const double ys_g = status[k] ? r[k] / den : 0.0, ys_b = status[k] ? -x[k] / den : 0.0;
   const double ytt_g = ys_g + 0.5 * st * g[k], ytt_b = ys_b + 0.5 * st * b[k];   // Ys + j*Bc/2, Bc = b - jg
   const double t = (tap[k] == 0.0) ? 1.0 : tap[k];
   double sn, cs;
@@ -168,6 +169,8 @@ struct mapdn_env {
   // device-side staging buffers of the *_host entry points
   double *d_stage_actions = nullptr, *d_stage_reward = nullptr, *d_stage_info = nullptr, *d_stage_obs = nullptr;
   unsigned char* d_stage_term = nullptr;
+  int obs_zero_off = 0;                // slab offset of the constant-zero slot the obs padding reads
+  std::vector<const void*> pinned_ok;  // host buffers already verified as pinned (mapdn_step_host_pinned)
 };
 
 namespace {
@@ -200,12 +203,17 @@ std::vector<T> vec_or(const T* p, size_t n, T fill) {
 }
 
 using KernelFn = void (*)(const Params);
+#ifndef MAPDN_HELPER_PAIRS_PER_WARP
+#define MAPDN_HELPER_PAIRS_PER_WARP 256
+#endif
+constexpr int kHelperPairsPerWarp = MAPDN_HELPER_PAIRS_PER_WARP;   // Box-Muller pairs of a CTA round per helper warp
 
 template <int G>
 KernelFn kernel_for_mode(int mode) {
   switch (mode) {
     case MODE_SOLVE: return env_kernel<G, MODE_SOLVE>;
     case MODE_STEP: return env_kernel<G, MODE_STEP>;
+    case MODE_DROOP: return env_kernel<G, MODE_DROOP>;
     default: return env_kernel<G, MODE_RESET>;
   }
 }
@@ -215,6 +223,7 @@ KernelFn kernel_for(int G, int mode, bool dense = false) {
     switch (mode) {
       case MODE_SOLVE: return env_kernel<32, MODE_SOLVE, true>;
       case MODE_STEP: return env_kernel<32, MODE_STEP, true>;
+      case MODE_DROOP: return env_kernel<32, MODE_DROOP, true>;
       default: return env_kernel<32, MODE_RESET, true>;
     }
   }
@@ -231,8 +240,18 @@ KernelFn kernel_for(int G, int mode, bool dense = false) {
 // smem per env in double2 units: (npq + 1) node records of 9 double2, sgen p/q, scratch of ng + 2 nl
 // doubles. For G = 4 two envs share a quarter-warp of a 128-bit access, so their slabs must start
 // 64 B apart modulo 128 B.
+// The prologue stages 2 n_load scaled load values per env. They fit the Newton fields of the node records (12 dead
+// doubles per record, see env_kernel.cuh) unless the net has very many loads per bus.
+bool stage_fits_records(int npq, int nl) { return 2 * nl <= 12 * (npq + 2); }
+
+// scratch doubles per env: next pv row / droop voltages [n_sgen], the partial sums per warp of the multi-warp group
+// reductions, and the staged loads when they do not fit the records
+int scratch_doubles_for(int npq, int ng, int nl, int G) {
+  return ng + (G > 32 ? 10 * (G / 32) : 0) + (stage_fits_records(npq, nl) ? 0 : 2 * nl);
+}
+
 int env_stride2_for(int npq, int ng, int nl, int G) {
-  int stride = kNodeArrays2 * (npq + 2) + ng + (ng + 2 * nl + 1) / 2;
+  int stride = kNodeArrays2 * (npq + 2) + ng + (scratch_doubles_for(npq, ng, nl, G) + 1) / 2;
   if (G == 4) while ((stride * 16) % 128 != 64) ++stride;
   return stride;
 }
@@ -498,7 +517,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
         if (i < 0) { esched.push_back(static_cast<uint64_t>(trash) | (static_cast<uint64_t>(npq) << 16) |
                                       (static_cast<uint64_t>(npq) << 32) | (static_cast<uint64_t>(kEschedReg0 | kEschedIdle) << 48)); continue; }
         lane_of[i] = sidx % G; step_of[i] = cur + sidx / G;
-        uint64_t c0 = npq, c1 = npq, fl = kEschedLoad0;      // no child: child 0 = the all-zero sentinel record
+        uint64_t c0 = npq, c1 = npq, fl = kEschedLeaf;       // no child: zero update, nothing to fetch
         if (nchild[i] > 2) {
           c0 = cfirst[i]; c1 = cfirst[i] + 1; fl = static_cast<uint64_t>(std::min(nchild[i] - 2, 255)) | kEschedLoad0 | kEschedLoad1;
           if (nchild[i] - 2 > 255) return bail(fail(MAPDN_ERR_UNSUPPORTED, "a bus with more than 257 children"));
@@ -516,10 +535,19 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     // a bus stores its Schur update only if its parent will fetch it from shared memory
     for (int i = 0; i < npq; ++i)
       if (parent[i] >= 0 && reg_child[parent[i]] != i) esched[epos[i]] |= static_cast<uint64_t>(kEschedStore) << 48;
-    // back sweep by depth: children inherit the lane of their parent (the child with the tallest subtree first)
+    // back sweep by depth (step 0 = the roots, whose "parent" is the all-zero sentinel record): children inherit the
+    // lane of their parent (the child with the tallest subtree first). The sweep also applies the Newton update to
+    // the bus it solves, so every bus appears exactly once.
     std::fill(lane_of.begin(), lane_of.end(), -1); std::fill(step_of.begin(), step_of.end(), -1);
+    std::vector<int> bpos(npq, -1);
+    std::vector<char> regp(npq, 0);
     cur = 0;
-    for (int l = 1; l < n_lev; ++l) {
+#ifdef MAPDN_FUSED_UPDATE
+    const int first_back_level = 0;
+#else
+    const int first_back_level = 1;      // the roots' dx = D^-1 r is already in place
+#endif
+    for (int l = first_back_level; l < n_lev; ++l) {
       const int w = dlev[l + 1] - dlev[l], nst = (w + G - 1) / G;
       std::vector<int> slot(static_cast<size_t>(nst) * G, -1);
       std::vector<char> reg(npq, 0);
@@ -529,31 +557,43 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
       std::vector<int> rest;
       for (int i : nodes) {
         const int pa = parent[i];
-        if (step_of[pa] == cur - 1 && lane_of[pa] >= 0 && slot[lane_of[pa]] < 0) { slot[lane_of[pa]] = i; reg[i] = 1; }
+        if (pa >= 0 && step_of[pa] == cur - 1 && lane_of[pa] >= 0 && slot[lane_of[pa]] < 0) { slot[lane_of[pa]] = i; reg[i] = 1; }
         else rest.push_back(i);
       }
       size_t pos = 0;
       for (int i : rest) { while (slot[pos] >= 0) ++pos; slot[pos] = i; }
       for (int sidx = 0; sidx < nst * G; ++sidx) {
         const int i = slot[sidx];
-        if (i < 0) { bsched.push_back(static_cast<uint64_t>(trash) | (static_cast<uint64_t>(npq) << 16) | (3ull << 32)); continue; }
+        if (i < 0) {
+          bsched.push_back(static_cast<uint64_t>(trash) | (static_cast<uint64_t>(npq) << 16) |
+                           (static_cast<uint64_t>(kBschedRegParent | kBschedIdle) << 32));
+          continue;
+        }
         lane_of[i] = sidx % G; step_of[i] = cur + sidx / G;
-        bsched.push_back(static_cast<uint64_t>(i) | (static_cast<uint64_t>(parent[i]) << 16) |
-                         (static_cast<uint64_t>(reg[i] && sidx / G == 0) << 32));
+        regp[i] = reg[i] && sidx / G == 0;
+        bpos[i] = static_cast<int>(bsched.size());
+        bsched.push_back(static_cast<uint64_t>(i) | (static_cast<uint64_t>(parent[i] >= 0 ? parent[i] : npq) << 16) |
+                         (static_cast<uint64_t>(regp[i] ? kBschedRegParent : 0u) << 32));
       }
       cur += nst;
     }
+    // a bus stores its dx only if a child will fetch it from shared memory (roots: D^-1 r is already in place)
+    for (int i = 0; i < npq; ++i)
+      if (parent[i] >= 0 && !regp[i] && parent[parent[i]] >= 0) bsched[bpos[parent[i]]] |= static_cast<uint64_t>(kBschedStoreX) << 32;
   }
   if (getenv("MAPDN_DEBUG_SCHED")) {
     int nreg = 0, nl0 = 0, nl1 = 0, nreal = 0;
     for (uint64_t e2 : esched) { if ((e2 & 0xFFFF) == (uint64_t)trash) continue; ++nreal; unsigned fl = e2 >> 48; nreg += !!(fl & kEschedReg0); nl0 += !!(fl & kEschedLoad0); nl1 += !!(fl & kEschedLoad1); }
     int breg = 0, breal = 0;
     for (uint64_t b2 : bsched) { if ((b2 & 0xFFFF) == (uint64_t)trash) continue; ++breal; breg += (b2 >> 32) & 1; }
+    { int nsx = 0; for (uint64_t b2 : bsched) nsx += ((b2 >> 32) & kBschedStoreX) ? 1 : 0; fprintf(stderr, "[sched] back sweep: %d buses store dx\n", nsx); }
     fprintf(stderr, "[sched] G=%d levels=%d esteps=%zu real=%d reg0=%d load0=%d load1=%d | bsteps=%zu real=%d regp=%d\n", G, n_lev,
             esched.size() / G, nreal, nreg, nl0, nl1, bsched.size() / G, breal, breg);
   }
+  if (bsched.empty())      // a forest of single buses: one all-idle step
+    bsched.assign(G, static_cast<uint64_t>(trash) | (static_cast<uint64_t>(npq) << 16) |
+                         (static_cast<uint64_t>(kBschedRegParent | kBschedIdle) << 32));
   const int n_esteps = static_cast<int>(esched.size()) / G, n_bsteps = static_cast<int>(bsched.size()) / G;
-  if (bsched.empty()) bsched.assign(G, static_cast<uint64_t>(trash) | (static_cast<uint64_t>(npq) << 16) | (3ull << 32));
 
   // ---- 3. element -> node maps (needed by the hot blob) ----
   const int na = npq + 2;      // + sentinel + trash records
@@ -588,7 +628,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     obs_dim = std::max(obs_dim, nz * (2 * ss_dem + ss_vm + ss_va) + ss_pv + ss_q);
   }
   const int pvq_off2 = kNodeArrays2 * na, scratch_off2 = pvq_off2 + ng;
-  if (2 * (scratch_off2 + (ng + 2 * nl + 1) / 2) >= 65535)
+  if (2 * (scratch_off2 + (scratch_doubles_for(npq, ng, nl, G) + 1) / 2) >= 65535)
     return bail(fail(MAPDN_ERR_UNSUPPORTED, "network too large for 16-bit slab offsets"));
   std::vector<uint16_t> obs_off(static_cast<size_t>(ng) * obs_dim);
   std::vector<unsigned> obs_src(static_cast<size_t>(ng) * obs_dim, 0u);
@@ -669,23 +709,24 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   {
     int off = 0;
     auto take = [&](size_t bytes) { int o = off; off += static_cast<int>((bytes + 15) / 16 * 16); return o; };
-    hl.yup = take(16 * npq); hl.ydn = take(16 * npq); hl.yii = take(16 * npq); hl.ysl = take(16 * npq);
+    hl.yup = take(16 * npq); hl.ydn = take(16 * (npq + 1)); hl.yii = take(16 * npq);
     hl.ndesc = take(8 * npq); hl.esched = take(8 * esched.size()); hl.bsched = take(8 * bsched.size());
     hl.lptr = take(2 * lptr.size()); hl.lidx = take(2 * lidx.size());
     hl.sptr = take(2 * sptr.size()); hl.sidx = take(2 * sidx.size());
     hl.xptr = take(2 * xptr.size()); hl.xidx = take(2 * std::max<size_t>(1, xidx.size()));
-    hl.node_of_bus = take(2 * n); hl.obs_off = take(2 * obs_off.size());
-    hl.line_nodes = take(2 * std::max<size_t>(1, line_nodes.size())); hl.line_c = take(8 * std::max<size_t>(1, line_c.size()));
+    hl.node_of_bus = take(2 * n);
     hl.nbr_ptr = take(2 * nbr_ptr.size()); hl.nbr_idx = take(2 * std::max<size_t>(1, nbr_idx.size()));
     hl.nbr_y = take(8 * std::max<size_t>(2, nbr_y.size()));
     hl.bytes = off;
   }
   std::vector<unsigned char> hot(hl.bytes, 0);
+  std::vector<double> ysl_cold(2 * static_cast<size_t>(npq), 0.0);     // Y[i,slack]: cold table, non-zero for a few buses
   std::vector<int> sl_node;
   std::vector<double> sl_y;
   {
     double* yup = reinterpret_cast<double*>(hot.data() + hl.yup); double* ydn = reinterpret_cast<double*>(hot.data() + hl.ydn);
-    double* yii = reinterpret_cast<double*>(hot.data() + hl.yii); double* ysl = reinterpret_cast<double*>(hot.data() + hl.ysl);
+    double* yii = reinterpret_cast<double*>(hot.data() + hl.yii);
+    double* ysl = ysl_cold.data();
     uint64_t* ndesc = reinterpret_cast<uint64_t*>(hot.data() + hl.ndesc);
     for (int i = 0; i < npq; ++i) {
       const int b = order[i];
@@ -704,7 +745,8 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
       const uint64_t pa = parent[i] >= 0 ? static_cast<uint64_t>(parent[i]) : npq;   // roots: sentinel, Y = 0
       const uint64_t c0 = nchild[i] > 0 ? cfirst[i] : npq, c1 = nchild[i] > 1 ? cfirst[i] + 1 : npq;
       const uint64_t nx = nchild[i] > 2 ? nchild[i] - 2 : 0;
-      ndesc[i] = pa | (c0 << 16) | (c1 << 32) | (nx << 48);
+      const uint64_t sl_adj = pairs.count({std::min(b, slack), std::max(b, slack)}) ? 1 : 0;
+      ndesc[i] = pa | (c0 << 16) | (c1 << 32) | (nx << 48) | (sl_adj << 63);
     }
     std::memcpy(hot.data() + hl.esched, esched.data(), 8 * esched.size());
     std::memcpy(hot.data() + hl.bsched, bsched.data(), 8 * bsched.size());
@@ -716,15 +758,10 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     if (!xidx.empty()) std::memcpy(hot.data() + hl.xidx, xidx.data(), 2 * xidx.size());
     uint16_t* nob = reinterpret_cast<uint16_t*>(hot.data() + hl.node_of_bus);
     for (int b = 0; b < n; ++b) nob[b] = static_cast<uint16_t>(node_of_bus[b]);
-    std::memcpy(hot.data() + hl.obs_off, obs_off.data(), 2 * obs_off.size());
     std::memcpy(hot.data() + hl.nbr_ptr, nbr_ptr.data(), 2 * nbr_ptr.size());
     if (!nbr_idx.empty()) {
       std::memcpy(hot.data() + hl.nbr_idx, nbr_idx.data(), 2 * nbr_idx.size());
       std::memcpy(hot.data() + hl.nbr_y, nbr_y.data(), 8 * nbr_y.size());
-    }
-    if (n_line) {
-      std::memcpy(hot.data() + hl.line_nodes, line_nodes.data(), 2 * line_nodes.size());
-      std::memcpy(hot.data() + hl.line_c, line_c.data(), 8 * line_c.size());
     }
   }
 
@@ -735,7 +772,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   const size_t max_smem = dp.sharedMemPerBlockOptin;
   // envs per CTA: sub-warp groups pack 32/G envs into each of 1..4 solver warps; multi-warp groups (G = 64 / 128)
   // put 1..4 envs of G threads in a CTA. Fewer envs per CTA when that spreads the batch over all SMs.
-  auto smem_for = [&](int epb) { return static_cast<size_t>(hl.bytes) + static_cast<size_t>(epb) * stride2 * 16; };
+  auto smem_for = [&](int epb) { return static_cast<size_t>(hl.bytes) + static_cast<size_t>(epb) * (stride2 * 16 + 16); };   // + helper scalars
   const int unit = (G <= 32) ? 32 / G : 1;               // envs added per step of the search
   // measured on B200 (profiles/): two solver warps per CTA for small sub-warp groups, four for one-warp envs,
   // as many multi-warp envs as fit (<= 512 solver threads)
@@ -763,10 +800,10 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   {   // helper warps (next profile rows + noise, concurrent with the Newton iteration): one per 256 Box-Muller pairs of a
       // CTA round, at most 4 -- a single warp was the critical path of case322 (197 -> 169 us with two)
     const int n_pair = (ng + 2 * nl + 1) / 2;
-    e->helper_threads = 32 * std::min(4, std::max(1, (epb * n_pair + 255) / 256));
+    e->helper_threads = 32 * std::min(4, std::max(1, (epb * n_pair + kHelperPairsPerWarp - 1) / kHelperPairsPerWarp));
   }
   if (const char* ov = getenv("MAPDN_HELPERS")) e->helper_threads = 32 * std::min(4, std::max(1, atoi(ov)));   // tuning override
-  for (int mode = 0; mode < 3; ++mode) {
+  for (int mode = 0; mode < 4; ++mode) {
     KernelFn fn = kernel_for(G, mode, meshed);
     // the attribute belongs to the function, not to the handle: always allow the device maximum, so that creating a
     // second handle with a smaller footprint cannot break the launches of the first
@@ -791,11 +828,38 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   P.n_esteps = n_esteps; P.n_bsteps = n_bsteps; P.has_extra_children = max_children > 2;
   P.slack_bus = slack;
   P.nb = cfg->batch; P.env_stride2 = stride2; P.pvq_off2 = pvq_off2; P.scratch_off2 = scratch_off2; P.hot_layout = hl;
+  P.helper_off = hl.bytes + e->epb * stride2 * 16;
+  P.stage_in_records = stage_fits_records(npq, nl) ? 1 : 0;
+  P.obs_skip_off = -1;
+  e->obs_zero_off = 2 * (npq * kNodeArrays2 + A_UP);
+  {   // bus shunts by node (res_bus p/q carry the shunt power, pandapower _get_shunt_results)
+    std::vector<double> sh_g(npq + 1), sh_b(npq + 1);
+    bool any = false;
+    for (int i = 0; i <= npq; ++i) {
+      const int b = (i == npq) ? slack : order[i];
+      sh_g[i] = gs[b]; sh_b[i] = bs[b];
+      any = any || gs[b] != 0.0 || bs[b] != 0.0;
+    }
+    P.has_shunt = any;
+    TRY(dev_upload(e, sh_g, &P.sh_g)); TRY(dev_upload(e, sh_b, &P.sh_b));
+  }
   std::vector<int> bus_of_node(order.begin(), order.end());
   TRY(dev_upload(e, hot, &P.hot));
   TRY(dev_upload(e, bus_of_node, &P.bus_of_node));
   TRY(dev_upload(e, lscale, &P.lscale)); TRY(dev_upload(e, sscale, &P.sscale));
   TRY(dev_upload(e, sl_node, &P.sl_node)); TRY(dev_upload(e, sl_y, &P.sl_y));
+  {
+    const double* d_ysl = nullptr;
+    TRY(dev_upload(e, ysl_cold, &d_ysl));
+    P.ysl = reinterpret_cast<const double2*>(d_ysl);
+    if (line_nodes.empty()) { line_nodes.assign(2, 0); line_c.assign(4, 0.0); }
+    TRY(dev_upload(e, obs_off, &P.obs_off)); TRY(dev_upload(e, line_nodes, &P.line_nodes)); TRY(dev_upload(e, line_c, &P.line_c));
+  }
+  {
+    std::vector<int> sgen_node(ng);
+    for (int j = 0; j < ng; ++j) sgen_node[j] = node_of_bus[net->sgen_bus[j]];
+    TRY(dev_upload(e, sgen_node, &P.sgen_node));
+  }
   TRY(dev_upload(e, state_src, &P.state_src)); TRY(dev_upload(e, obs_src, &P.obs_src)); TRY(dev_upload(e, obs_xptr, &P.obs_xptr)); TRY(dev_upload(e, obs_xidx, &P.obs_xidx));
   const size_t B = static_cast<size_t>(cfg->batch);
   if (prof) {
@@ -839,7 +903,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   TRY(dev_alloc(e, B * n, &P.res_p)); TRY(dev_alloc(e, B * n, &P.res_q));
   TRY(dev_alloc(e, B * std::max(1, n_line), &P.res_pl));
   TRY(dev_alloc(e, B, &P.steps)); TRY(dev_alloc(e, B, &P.sum_rewards));
-  TRY(dev_alloc(e, B, &P.start_row)); TRY(dev_alloc(e, B, &P.episode));
+  TRY(dev_alloc(e, B, &P.start_row)); TRY(dev_alloc(e, B, &P.episode)); TRY(dev_alloc(e, B, &P.nr_iters));
   if (meshed) {
     const size_t m = 2 * static_cast<size_t>(npq);
     P.dense_stride = static_cast<int>(m * (m + 1));
@@ -857,6 +921,9 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   // read p_load,q_load,p_pv,a ; write vm,va ; write obs ; reward+done+11 info
   d.algorithmic_bytes_per_env_step = 8LL * (2 * nl + 2 * ng) + 8LL * 2 * n + 8LL * ng * obs_dim + 8LL * 13;
   (void)max_width;
+  // the memsets / uploads above ran on the legacy default stream: order them before any launch of the caller's
+  // (possibly non-blocking) streams
+  TRY_CUDA(cudaDeviceSynchronize());
   *out = e;
   return MAPDN_OK;
 #undef TRY
@@ -872,12 +939,13 @@ mapdn_status mapdn_get_dims(const mapdn_env* e, mapdn_dims* out) {
 int64_t mapdn_launch_count(const mapdn_env* e) { return e ? e->launches : 0; }
 
 mapdn_status mapdn_reset(mapdn_env* e, const int32_t* start_dhi_dev, const uint8_t* mask_dev, int32_t add_noise,
-                         double* obs_dev, double* state_dev, void* stream) {
+                         double* obs_dev, double* state_dev, uint8_t* converged_dev, void* stream) {
   if (!e) return fail(MAPDN_ERR_INVALID, "null handle");
   if (!e->base.prof_pv) return fail(MAPDN_ERR_INVALID, "handle was created without a profile store");
   MAPDN_ON_DEVICE(e->device);
   Params p = e->base;
   p.start_dhi = start_dhi_dev; p.mask = mask_dev; p.add_noise = add_noise; p.obs = obs_dev; p.state = state_dev;
+  p.reset_ok = converged_dev;
   return launch_env_kernel(e, MODE_RESET, p, static_cast<cudaStream_t>(stream));
 }
 
@@ -907,6 +975,53 @@ mapdn_status mapdn_step_host(mapdn_env* e, const double* actions_host, int32_t a
   if (info_host) MAPDN_CUDA(cudaMemcpyAsync(info_host, e->d_stage_info, B * MAPDN_N_INFO * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (obs_host) MAPDN_CUDA(cudaMemcpyAsync(obs_host, e->d_stage_obs, B * ng * od * sizeof(double), cudaMemcpyDeviceToHost, st));
   MAPDN_CUDA(cudaStreamSynchronize(st));
+  return MAPDN_OK;
+}
+
+// device alias of a pinned host buffer (unified addressing); verified once per buffer
+static mapdn_status pinned_alias(mapdn_env* e, const void* host, void** dev, const char* what) {
+  *dev = const_cast<void*>(host);
+  if (!host) return MAPDN_OK;
+  if (std::find(e->pinned_ok.begin(), e->pinned_ok.end(), host) != e->pinned_ok.end()) return MAPDN_OK;
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess || at.type != cudaMemoryTypeHost || at.devicePointer != host) {
+    cudaGetLastError();
+    return fail(MAPDN_ERR_INVALID, std::string(what) + ": not page-locked host memory with unified addressing "
+                                   "(cudaHostAlloc / cudaHostRegister it, or use mapdn_step_host)");
+  }
+  if (e->pinned_ok.size() < 64) e->pinned_ok.push_back(host);
+  return MAPDN_OK;
+}
+
+mapdn_status mapdn_step_host_pinned(mapdn_env* e, const double* actions_host, int32_t add_noise, double* reward_host,
+                                    uint8_t* terminated_host, double* info_host, void* obs_host, int32_t obs_is_f32,
+                                    int32_t skip_padding, int32_t sync, void* stream) {
+  if (!e || !actions_host || !reward_host || !terminated_host) return fail(MAPDN_ERR_INVALID, "null argument");
+  if (!e->base.prof_pv) return fail(MAPDN_ERR_INVALID, "handle was created without a profile store");
+  MAPDN_ON_DEVICE(e->device);
+  void *a, *r, *t, *i, *o;
+  mapdn_status s;
+  if ((s = pinned_alias(e, actions_host, &a, "actions_host")) != MAPDN_OK) return s;
+  if ((s = pinned_alias(e, reward_host, &r, "reward_host")) != MAPDN_OK) return s;
+  if ((s = pinned_alias(e, terminated_host, &t, "terminated_host")) != MAPDN_OK) return s;
+  if ((s = pinned_alias(e, info_host, &i, "info_host")) != MAPDN_OK) return s;
+  if ((s = pinned_alias(e, obs_host, &o, "obs_host")) != MAPDN_OK) return s;
+  Params p = e->base;
+  p.actions = static_cast<const double*>(a); p.add_noise = add_noise; p.reward = static_cast<double*>(r);
+  p.term = static_cast<unsigned char*>(t); p.info = static_cast<double*>(i);
+  p.obs = obs_is_f32 ? nullptr : static_cast<double*>(o);
+  p.obs32 = obs_is_f32 ? static_cast<float*>(o) : nullptr;
+  p.obs_skip_off = skip_padding ? e->obs_zero_off : -1;
+  s = launch_env_kernel(e, MODE_STEP, p, static_cast<cudaStream_t>(stream));
+  if (s != MAPDN_OK) return s;
+  if (sync) MAPDN_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  return MAPDN_OK;
+}
+
+mapdn_status mapdn_wait(mapdn_env* e, void* stream) {
+  if (!e) return fail(MAPDN_ERR_INVALID, "null handle");
+  MAPDN_ON_DEVICE(e->device);
+  MAPDN_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
   return MAPDN_OK;
 }
 
@@ -988,6 +1103,10 @@ mapdn_status mapdn_get_field(mapdn_env* e, int32_t field, double* out_dev, void*
       int_to_double_kernel<<<static_cast<unsigned>((B + 255) / 256), 256, 0, st>>>(B, p.steps, out_dev);
       MAPDN_CUDA(cudaGetLastError()); e->launches++;
       return MAPDN_OK;
+    case MAPDN_FIELD_NR_ITERS:
+      int_to_double_kernel<<<static_cast<unsigned>((B + 255) / 256), 256, 0, st>>>(B, p.nr_iters, out_dev);
+      MAPDN_CUDA(cudaGetLastError()); e->launches++;
+      return MAPDN_OK;
     case MAPDN_FIELD_START_ROW:
       i64_to_double_kernel<<<static_cast<unsigned>((B + 255) / 256), 256, 0, st>>>(B, p.start_row, out_dev);
       MAPDN_CUDA(cudaGetLastError()); e->launches++;
@@ -1013,6 +1132,23 @@ mapdn_status mapdn_solve(mapdn_env* e, int32_t nb, const double* p_load, const d
   p.out_vm = vm; p.out_va = va_deg; p.out_p = p_bus; p.out_q = q_bus; p.out_pl = pl;
   p.out_iters = iters; p.out_conv = converged;
   return launch_env_kernel(e, MODE_SOLVE, p, static_cast<cudaStream_t>(stream));
+}
+
+mapdn_status mapdn_droop(mapdn_env* e, int32_t nb, const double* p_load, const double* q_load, const double* p_sgen,
+                         const double* s_rated, const double* q_max_manual, double gain, double tol, int32_t max_ite,
+                         double* vm, double* q_sgen, double* loss, int32_t* iterations, void* stream) {
+  if (!e || nb < 1 || !p_sgen || !s_rated || !q_max_manual || !q_sgen || !loss || !iterations ||
+      (e->dims.n_load > 0 && (!p_load || !q_load)))
+    return fail(MAPDN_ERR_INVALID, "null argument");
+  if (max_ite < 1 || !(gain > 0.0)) return fail(MAPDN_ERR_INVALID, "droop: need max_ite >= 1 and gain > 0");
+  MAPDN_ON_DEVICE(e->device);
+  Params p = e->base;
+  p.nb = nb;
+  p.in_pl = p_load; p.in_ql = q_load; p.in_pv = p_sgen; p.in_q = nullptr;
+  p.droop_s = s_rated; p.droop_qmm = q_max_manual; p.droop_gain = gain; p.droop_tol = tol; p.droop_max_ite = max_ite;
+  p.out_vm = vm; p.out_va = nullptr; p.out_p = nullptr; p.out_q = nullptr; p.out_pl = nullptr;
+  p.out_iters = iterations; p.out_conv = nullptr; p.droop_q_out = q_sgen; p.droop_loss_out = loss;
+  return launch_env_kernel(e, MODE_DROOP, p, static_cast<cudaStream_t>(stream));
 }
 
 mapdn_status mapdn_get_ybus_dense(mapdn_env* e, double* g_host, double* b_host) {

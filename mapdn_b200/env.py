@@ -115,6 +115,7 @@ class BatchedVoltageControl:
             self.reward = torch.zeros(B, dtype=f64, device=self.device)
             self.terminated = torch.zeros(B, dtype=torch.uint8, device=self.device)
             self.info = torch.zeros(B, len(INFO_KEYS), dtype=f64, device=self.device)
+            self.reset_ok = torch.ones(B, dtype=torch.uint8, device=self.device)
         self._hist = None       # [B, history, n_agents, obs_dim] ring of the last observations (history > 1)
         self._host = None
         # raw pointers of the internal buffers (ctypes converts plain ints for c_void_p parameters): keeps the
@@ -150,17 +151,37 @@ class BatchedVoltageControl:
 
     # ---- reset / step -----------------------------------------------------------------------
     def reset(self, start: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
-              add_noise: bool = True):
+              add_noise: bool = True, check: bool = False, max_retries: int = 8, want_state: bool = True):
         """``start``: int32 ``[B,3]`` (day, hour, interval) = ``manual_reset`` per env, or None to
         sample (reference :111-113). ``mask``: uint8 ``[B]`` selecting the envs to reset.
-        Returns (obs ``[B,n_agents,obs_dim]``, state ``[B,state_dim]``) - views of internal buffers."""
+        Returns (obs ``[B,n_agents,obs_dim]``, state ``[B,state_dim]``) - views of internal buffers.
+
+        The reference re-draws an env until its initial power flow converges (:108-133). The device does up to 16
+        draws per call and records the outcome in ``self.reset_ok`` (uint8 ``[B]``, stream-ordered, no host sync).
+        ``check=True`` reads it back (one host sync), repeats the reset for the envs that are still unsolved (sampled
+        starts only) and raises ``MapdnError`` after ``max_retries`` rounds - the B = 1 shim does this."""
         if start is not None:
             self._chk(start, (self.batch, 3), torch.int32, "start")
         if mask is not None:
             self._chk(mask, (self.batch,), torch.uint8, "mask")
+        p_state = _ptr(self.state) if want_state else None          # rollouts that never read get_state skip it
         _capi.check(self._L.mapdn_reset(self._h, _ptr(start), _ptr(mask), int(add_noise), _ptr(self.obs),
-                                        _ptr(self.state), self._stream()))
-        if mask is not None:   # state of the untouched envs
+                                        p_state, _ptr(self.reset_ok), self._stream()))
+        if check:
+            sel = torch.ones_like(self.reset_ok) if mask is None else mask
+            for _ in range(max_retries + 1):
+                bad = ((self.reset_ok == 0) & (sel != 0)).to(torch.uint8)
+                if not bool(bad.any()):
+                    break
+                if start is not None:
+                    raise MapdnError("manual_reset: the power flow of the requested start does not converge")
+                _capi.check(self._L.mapdn_reset(self._h, None, _ptr(bad), int(add_noise), _ptr(self.obs),
+                                                p_state, _ptr(self.reset_ok), self._stream()))
+                sel = bad
+            else:
+                raise MapdnError(f"reset: {int(bad.sum())} env(s) found no solvable start in "
+                                 f"{16 * (max_retries + 1)} draws")
+        if mask is not None and want_state:   # state of the untouched envs
             _capi.check(self._L.mapdn_get_state(self._h, _ptr(self.state), self._stream()))
         if self.history > 1:
             if self._hist is None or mask is None:
@@ -200,20 +221,44 @@ class BatchedVoltageControl:
                 obs32=torch.zeros(B, self.n_agents, self.obs_size, dtype=torch.float32, **pin))
         return self._host
 
-    def step_host(self, actions: np.ndarray, add_noise: bool = True, obs_dtype=np.float64):
-        """NumPy in / NumPy out: H2D(actions) + fused step + D2H(reward, terminated, info, obs).
-        ``obs_dtype=np.float32`` delivers the observations in fp32 (what the reference's learners use after
-        ``prep_obs``), halving the device->host traffic. Returns views of pinned host buffers (overwritten by the
-        next call)."""
+    def step_host(self, actions: np.ndarray, add_noise: bool = True, obs_dtype=np.float64, staged: bool = False,
+                  sync: bool = True):
+        """NumPy in / NumPy out. Default: the zero-copy path (``mapdn_step_host_pinned``) - the fused kernel reads the
+        actions from and writes reward / terminated / info / observations straight to this object's pinned host
+        buffers, so the PCIe transfer overlaps the kernel; the never-changing zero padding of the observation rows is
+        not rewritten. ``staged=True``: the round-1 path (H2D copy, kernel, four D2H copies). ``obs_dtype=np.float32``
+        delivers the observations in fp32 (what the reference's learners use after ``prep_obs``). ``sync=False`` returns
+        right after the launch - call :meth:`wait` before reading the results. Returns views of pinned host buffers
+        (overwritten by the next call)."""
         hb = self._host_buffers()
         hb["actions"].numpy()[...] = actions
         f32 = np.dtype(obs_dtype) == np.float32
-        fn = self._L.mapdn_step_host_f32obs if f32 else self._L.mapdn_step_host
         obs = hb["obs32"] if f32 else hb["obs"]
-        _capi.check(fn(self._h, hb["actions"].data_ptr(), int(add_noise), hb["reward"].data_ptr(),
-                       hb["terminated"].data_ptr(), hb["info"].data_ptr(), obs.data_ptr(),
-                       torch.cuda.current_stream(self.device).cuda_stream))
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        if staged:
+            fn = self._L.mapdn_step_host_f32obs if f32 else self._L.mapdn_step_host
+            _capi.check(fn(self._h, hb["actions"].data_ptr(), int(add_noise), hb["reward"].data_ptr(),
+                           hb["terminated"].data_ptr(), hb["info"].data_ptr(), obs.data_ptr(), stream))
+        else:
+            _capi.check(self._L.mapdn_step_host_pinned(self._h, hb["actions"].data_ptr(), int(add_noise),
+                                                       hb["reward"].data_ptr(), hb["terminated"].data_ptr(),
+                                                       hb["info"].data_ptr(), obs.data_ptr(), int(f32), 1, int(sync), stream))
         return hb["reward"].numpy(), hb["terminated"].numpy(), hb["info"].numpy(), obs.numpy()
+
+    def wait(self):
+        """Blocks until the results of a ``step_host(..., sync=False)`` are in the host buffers."""
+        _capi.check(self._L.mapdn_wait(self._h, torch.cuda.current_stream(self.device).cuda_stream))
+
+    @property
+    def host_obs_bytes_per_env(self) -> int:
+        """fp64 bytes of one env's observations that are not padding (what the zero-copy host path moves)."""
+        if getattr(self, "_obs_used", None) is None:
+            zones = [int((self.net.bus_zone == z).sum()) for z in self.net.sgen_zone]
+            ss = set(self.args["state_space"])
+            per = [nz * (2 * ("demand" in ss) + ("vm_pu" in ss) + ("va_degree" in ss)) + ("pv" in ss) + ("reactive" in ss)
+                   for nz in zones]
+            self._obs_used = 8 * int(sum(per))
+        return self._obs_used
 
     def get_obs_stacked(self) -> torch.Tensor:
         """``history`` stacked observations ``[B, n_agents, history * obs_dim]``, oldest frame first and zero frames
@@ -235,7 +280,7 @@ class BatchedVoltageControl:
         d = self.dims
         width = dict(vm=d["n_bus"], va_deg=d["n_bus"], p_bus=d["n_bus"], q_bus=d["n_bus"], p_sgen=d["n_sgen"],
                      q_sgen=d["n_sgen"], line_loss=d["n_line"], p_load=d["n_load"], q_load=d["n_load"],
-                     sum_rewards=1, steps=1, start_row=1)[name]
+                     sum_rewards=1, steps=1, start_row=1, nr_iters=1)[name]
         out = torch.empty(self.batch, width, dtype=torch.float64, device=self.device)
         _capi.check(self._L.mapdn_get_field(self._h, _capi.FIELDS[name], _ptr(out), self._stream()))
         return out
@@ -338,9 +383,9 @@ class VoltageControl:
 
     def reset(self, reset_time=True):
         if reset_time or not hasattr(self, "_last_start"):
-            self._env.reset(None, add_noise=True)
+            self._env.reset(None, add_noise=True, check=True)
         else:
-            self._env.reset(self._last_start, add_noise=True)
+            self._env.reset(self._last_start, add_noise=True, check=True)
         start = int(self._env.get_field("start_row").item())
         sph = self._env.profiles.steps_per_hour
         self._episode_start_day, rem = divmod(start, 24 * sph)
@@ -350,9 +395,15 @@ class VoltageControl:
         return self._after_reset()
 
     def manual_reset(self, day, hour, interval):
+        sph, prof = self._env.profiles.steps_per_hour, self._env.profiles
+        start = interval + hour * sph + day * 24 * sph
+        if not (0 <= hour < 24 and 0 <= interval < sph and day >= 0 and start + self.episode_limit <= prof.n_rows - 1):
+            # the reference would slice a short window here and fail later inside step (:440-468)
+            raise ValueError(f"manual_reset({day}, {hour}, {interval}): the episode window does not fit the "
+                             f"{prof.n_rows}-row profile store")
         self._episode_start_day, self._episode_start_hour, self._episode_start_interval = day, hour, interval
         self._last_start = torch.tensor([[day, hour, interval]], dtype=torch.int32, device=self._env.device)
-        self._env.reset(self._last_start, add_noise=False)          # reference :159
+        self._env.reset(self._last_start, add_noise=False, check=True)          # reference :159
         return self._after_reset()
 
     # ---- step ----------------------------------------------------------------------------------

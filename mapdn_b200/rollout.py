@@ -37,6 +37,8 @@ class DeviceReplayBuffer:
 
     def add_batch(self, obs, action, reward, next_obs, done):
         B = obs.shape[0]
+        if B > self.size:
+            raise ValueError(f"a batch of {B} transitions does not fit a buffer of {self.size} (duplicate ring indices)")
         idx = (self.head + torch.arange(B, device=self.device)) % self.size
         self.obs[idx] = obs.to(self.obs.dtype)
         self.next_obs[idx] = next_obs.to(self.obs.dtype)
@@ -61,11 +63,16 @@ class BatchedRollout:
     :class:`~mapdn_b200.env.BatchedVoltageControl`, with the reference's action translation and
     episode handling (terminated envs are re-drawn on the device, no host sync)."""
 
-    def __init__(self, env, policy: Callable[[torch.Tensor], torch.Tensor], buffer: Optional[DeviceReplayBuffer] = None):
+    def __init__(self, env, policy: Callable[[torch.Tensor], torch.Tensor], buffer: Optional[DeviceReplayBuffer] = None,
+                 keep_returns: int = 1 << 16):
         self.env, self.policy, self.buffer = env, policy, buffer
         self.scale, self.bias = env.args["action_scale"], env.args["action_bias"]
         self.episode_return = torch.zeros(env.batch, dtype=torch.float64, device=env.device)
-        self.finished_returns = []
+        # returns of finished episodes: a bounded ring on the device (the last `keep_returns`) + running sum / count
+        self.keep_returns = max(int(keep_returns), env.batch)
+        self._ret_ring = torch.zeros(self.keep_returns, dtype=torch.float64, device=env.device)
+        self._ret_n = torch.zeros((), dtype=torch.int64, device=env.device)          # episodes finished so far
+        self._ret_sum = torch.zeros((), dtype=torch.float64, device=env.device)
         self.info_sum = torch.zeros(env.batch, len(env.info[0]), dtype=torch.float64, device=env.device)
         self._started = False
 
@@ -85,14 +92,28 @@ class BatchedRollout:
                 self.buffer.add_batch(obs, raw.reshape(env.batch, env.n_agents), reward, next_obs, done)
             self.episode_return += reward
             self.info_sum += info
-            if self.finished_returns is not None:
-                self.finished_returns.append((done.clone(), self.episode_return.clone()))
+            d = done.to(torch.int64)                    # finished episodes -> ring slots, no host sync
+            slot = (self._ret_n + torch.cumsum(d, 0) - 1) % self.keep_returns
+            slot = torch.where(d.bool(), slot, torch.full_like(slot, self.keep_returns))      # dropped by the scatter
+            pad = torch.cat([self._ret_ring, self._ret_ring.new_zeros(1)])
+            pad[slot] = self.episode_return
+            self._ret_ring = pad[:-1]
+            self._ret_sum += (self.episode_return * d).sum()
+            self._ret_n += d.sum()
             self.episode_return = torch.where(done.bool(), torch.zeros_like(self.episode_return), self.episode_return)
-            env.reset(mask=done)                      # masked, stream-ordered: only terminated envs are re-drawn
+            env.reset(mask=done, want_state=False)                      # masked, stream-ordered: only terminated envs are re-drawn
             obs = torch.where(done.bool()[:, None, None], env.obs, next_obs)
         return obs
 
     def completed_episode_returns(self) -> torch.Tensor:
-        """Returns of all episodes that ended so far (one host sync)."""
-        out = [ret[d.bool()] for d, ret in self.finished_returns]
-        return torch.cat(out) if out else torch.zeros(0, dtype=torch.float64, device=self.env.device)
+        """Returns of the episodes that ended so far - the last ``keep_returns`` of them (one host sync)."""
+        n = int(self._ret_n)
+        if n <= self.keep_returns:
+            return self._ret_ring[:n].clone()
+        h = n % self.keep_returns
+        return torch.cat([self._ret_ring[h:], self._ret_ring[:h]])
+
+    def mean_episode_return(self) -> float:
+        """Mean return over ALL finished episodes (one host sync)."""
+        n = int(self._ret_n)
+        return float(self._ret_sum) / n if n else float("nan")

@@ -159,6 +159,10 @@ class PandapowerEquivalent:
         q_ext = Sinj[self.ref].imag + QD[self.ref]
         p[self.ref] = PD[self.ref] - p_ext
         q[self.ref] = QD[self.ref] - q_ext
+        # bus shunts appear in res_bus as demand at the solved voltage (pandapower results_bus._get_shunt_results:
+        # p += p_shunt * vm^2, q += q_shunt * vm^2 with ppc GS = p_shunt, BS = -q_shunt) [RECALLED]
+        p = p + n.bus_gs * res.vm_pu ** 2
+        q = q - n.bus_bs * res.vm_pu ** 2
         res.p_mw, res.q_mvar = p, q
         res.p_ext_mw, res.q_ext_mvar = p_ext, q_ext
         Sf = V[n.br_from] * np.conj(self.Yf @ V) * n.base_mva

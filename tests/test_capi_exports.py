@@ -25,13 +25,13 @@ def test_library_exports_every_declared_symbol(built_lib):
     for fn in declared_functions():
         assert hasattr(L, fn), f"{fn} declared in the header but not exported"
     L.mapdn_abi_version.restype = ctypes.c_int32
-    assert L.mapdn_abi_version() == 1
+    assert L.mapdn_abi_version() == 2
 
 
 def test_binding_covers_the_header(built_lib):
     from mapdn_b200 import _capi
     assert sorted(_capi.EXPORTS) == declared_functions()
-    assert _capi.lib().mapdn_abi_version() == 1
+    assert _capi.lib().mapdn_abi_version() == _capi.ABI_VERSION == 2
 
 
 def test_struct_layouts_match_header():

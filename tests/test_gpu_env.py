@@ -62,7 +62,8 @@ def test_golden_trajectory_case33():
 
 @pytest.mark.parametrize("name,barrier,lanes", [("case33", "bowl", 0), ("case33", "bump", 32), ("case33", "l2", 4),
                                                  ("case141", "l1", 0), ("case322", "courant_beltrami", 0),
-                                                 ("case141", "bowl", 64), ("case322", "l2", 128), ("case33", "l1", 64)])
+                                                 ("case141", "bowl", 64), ("case322", "l2", 128), ("case33", "l1", 64),
+                                                 ("case322", "bowl", 0)])      # BASELINE.json config 5
 @pytest.mark.parametrize("add_noise", [True, False])
 def test_trajectory_matches_oracle(name, barrier, lanes, add_noise):
     from oracle.voltage_control_ref import VoltageControlOracle

@@ -58,6 +58,31 @@ def test_droop_and_no_control_match_the_script():
     assert float(dev1) < float(dev0)
 
 
+@pytest.mark.parametrize("name,lanes", [("case33", 0), ("case141", 0), ("case322", 64)])
+def test_droop_kernel_is_one_launch_and_equals_the_host_loop(name, lanes):
+    """mapdn_droop (the whole relaxed loop inside the fused kernel) against the round-1 host-driven loop."""
+    from mapdn_b200.baselines import droop_control, droop_control_host_loop
+    from mapdn_b200.env import BatchedVoltageControl
+    net = cases.make_case(name)
+    B = 37
+    inp = cases.synthetic_inputs(name, B, seed=9)
+    env = BatchedVoltageControl(net, None, None, batch=1, lanes_per_env=lanes)
+    n0 = env.launch_count
+    out = droop_control(env, inp["p_load"], inp["q_load"], inp["p_pv"], inp["s_max"])
+    torch.cuda.synchronize()
+    assert env.launch_count - n0 == 1
+    ref = droop_control_host_loop(env, inp["p_load"], inp["q_load"], inp["p_pv"], inp["s_max"])
+    assert torch.equal(out["iterations"], ref["iterations"])
+    assert int(out["iterations"].min()) >= 2 and int(out["iterations"].max()) < 100
+    assert float((out["vm"] - ref["vm"]).abs().max()) < 1e-10
+    assert float((out["q"] - ref["q"]).abs().max()) < 1e-10
+    assert float((out["loss"] - ref["loss"]).abs().max()) < 1e-10
+    # the iteration cap: q of the last power flow, iterations == cap
+    capped = droop_control(env, inp["p_load"], inp["q_load"], inp["p_pv"], inp["s_max"], max_ite=3)
+    assert int(capped["iterations"].max()) == 3
+    env.close()
+
+
 def test_batched_rollout_with_replay_buffer():
     from mapdn_b200.env import BatchedVoltageControl
     from mapdn_b200.rollout import BatchedRollout, DeviceReplayBuffer

@@ -1,0 +1,122 @@
+"""The batched runner feeds the REFERENCE's own learner code (models/maddpg.py, utilities/trainer.py) unchanged.
+
+Runs where /root/reference exists (this container; it is imported in the test only, never by the product) on a CPU
+stand-in for BatchedVoltageControl; skipped on the GPU box. The GPU leg with the real env and an in-repo model of the
+same interface is tests/test_gpu_extras.py::test_marl_runner_on_device."""
+import os
+import sys
+from collections import namedtuple
+
+import numpy as np
+import pytest
+import torch
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "models")), reason="reference tree not present")
+
+
+class FakeBatchedEnv:
+    """CPU stand-in with the surface of BatchedVoltageControl the runner touches."""
+
+    def __init__(self, B, n_agents, obs_dim, episode_limit, seed=0):
+        self.batch, self.n_agents, self.n_actions, self.obs_size = B, n_agents, 1, obs_dim
+        self.device = torch.device("cpu")
+        self.g = torch.Generator().manual_seed(seed)
+        self.obs = torch.zeros(B, n_agents, obs_dim, dtype=torch.float64)
+        self.t = torch.zeros(B, dtype=torch.int64)
+        self.episode_limit = episode_limit
+        self.actions_seen = []
+
+    def reset(self, mask=None, want_state=True, **kw):
+        m = torch.ones(self.batch, dtype=torch.bool) if mask is None else mask.bool()
+        new = torch.rand(self.batch, self.n_agents, self.obs_size, generator=self.g, dtype=torch.float64)
+        self.obs = torch.where(m[:, None, None], new, self.obs)
+        self.t = torch.where(m, torch.ones_like(self.t), self.t)
+        return self.obs, None
+
+    def step(self, a):
+        assert a.dtype == torch.float64 and tuple(a.shape) == (self.batch, self.n_agents)
+        self.actions_seen.append(a.clone())
+        self.obs = torch.rand(self.batch, self.n_agents, self.obs_size, generator=self.g, dtype=torch.float64)
+        self.t += 1
+        reward = -a.abs().mean(dim=1)
+        done = (self.t >= self.episode_limit).to(torch.uint8)
+        info = torch.arange(11, dtype=torch.float64)[None, :].repeat(self.batch, 1)
+        return reward, done, info
+
+
+@pytest.fixture
+def reference_on_path():
+    """The reference imports its agents lazily (models/model.py:150-163) from namespace packages (no __init__.py); an
+    unrelated `agents` distribution in site-packages would shadow them, so the reference's directories are registered
+    as the packages for the duration of the test."""
+    import types
+    saved = {k: sys.modules.get(k) for k in ("agents", "critics", "models", "utilities")}
+    for k in saved:
+        for name in [m for m in sys.modules if m == k or m.startswith(k + ".")]:
+            del sys.modules[name]
+        pkg = types.ModuleType(k)
+        pkg.__path__ = [os.path.join(REF, k)]
+        sys.modules[k] = pkg
+    sys.path.append(REF)
+    yield
+    sys.path.remove(REF)
+    for k, v in saved.items():
+        for name in [m for m in sys.modules if m == k or m.startswith(k + ".")]:
+            del sys.modules[name]
+        if v is not None:
+            sys.modules[k] = v
+
+
+def _reference_maddpg(n_agents, obs_dim, max_steps):
+    import yaml
+    from models.maddpg import MADDPG
+    from utilities.trainer import PGTrainer
+    d = yaml.safe_load(open(os.path.join(REF, "args", "default.yaml")))
+    d.update(yaml.safe_load(open(os.path.join(REF, "args", "alg_args", "maddpg.yaml")))["alg_args"])
+    d.update(agent_num=n_agents, obs_size=obs_dim, action_dim=1, cuda=False, max_steps=max_steps, action_scale=0.8,
+             action_bias=0.0, batch_size=8)
+    args = namedtuple("Args", d.keys())(**d)
+    trainer = PGTrainer(args, MADDPG, env=None, logger=None)
+    return args, trainer
+
+
+def test_reference_maddpg_learns_from_device_batches(reference_on_path):
+    from mapdn_b200.marl_runner import BatchedMarlRunner, DeviceTransitionBuffer, attach
+    B, n, od, T = 5, 3, 7, 6
+    args, trainer = _reference_maddpg(n, od, max_steps=T)
+    net = attach(trainer.behaviour_net)
+    env = FakeBatchedEnv(B, n, od, episode_limit=4)
+    buf = DeviceTransitionBuffer(32, B, n, od, act_dim=1, hid_dim=args.hid_size, device=env.device)
+    updates = []
+
+    def update(runner, stat):                      # the reference's own optimisation steps on a device batch
+        if len(runner.buffer) >= 2 * args.batch_size:
+            batch = runner.buffer.get_batch(args.batch_size, n_windows=2)
+            w0 = [p.detach().clone() for p in trainer.behaviour_net.value_dicts.parameters()]
+            trainer.value_transition_process(stat, batch)
+            trainer.policy_transition_process(stat, batch)
+            updates.append(any(not torch.equal(a, b) for a, b in
+                               zip(w0, trainer.behaviour_net.value_dicts.parameters())))
+    runner = BatchedMarlRunner(env, net, buf, update_fn=update)
+    stat = runner.train_process({})
+    assert runner.steps == T * B and buf.count == T
+    # translate_action (utilities/util.py:123-132): every action the env saw lies inside [bias - scale, bias + scale]
+    a = torch.stack(env.actions_seen)
+    assert float(a.abs().max()) <= 0.8 + 1e-12
+    # transition layout == what Model.unpack_data would have produced
+    b = buf.latest(T)
+    st, ac, lp, v, nv, rw, ns, dn, ls, av, lh, h = b.unpacked()
+    assert st.shape == (T * B, n, od) and ac.shape == (T * B, n, 1) and v.shape == (T * B, n, 1) and rw.shape == (T * B, n)
+    assert dn.shape == (T * B, 1) and ls.shape == (T * B, 1) and av.shape == (T * B, n, 1) and lh.shape == (T * B, n, args.hid_size)
+    # done at the env's episode_limit (4 -> after 3 steps), last_step additionally at t = max_steps - 1 (model.py:225)
+    dn, ls = dn.view(T, B), ls.view(T, B)
+    assert bool((dn[2] == 1).all()) and bool((dn[[0, 1, 3, 4]] == 0).all())
+    assert bool((ls[T - 1] == 1).all()) and bool((ls[2] == 1).all()) and float(ls.sum()) == float(dn.sum()) + B * (1 - int(dn[T - 1, 0]))
+    # hidden state restarts at zero after a terminated episode
+    assert float(lh.view(T, B, n, -1)[3].abs().max()) == 0.0 and float(lh.view(T, B, n, -1)[1].abs().max()) > 0.0
+    # mean_train_* (model.py:243-261): info k is the constant k in the stand-in env
+    assert abs(stat["mean_train_total_line_loss"] - 8.0) < 1e-12 and "mean_train_reward" in stat
+    assert updates and all(updates) and "mean_train_value_loss" in stat and np.isfinite(stat["mean_train_value_loss"])
+    ev = runner.evaluation({}, num_eval_episodes=B)
+    assert abs(ev["mean_test_destroy"] - 10.0) < 1e-12 and np.isfinite(ev["mean_test_reward"])
