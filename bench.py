@@ -302,31 +302,6 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def bind_numa(local_rank):
-    """Pin this rank to the host cores next to its GPU (8-GPU boxes: GPU0-3 <-> NUMA0, GPU4-7 <-> NUMA1) BEFORE the
-    pinned staging buffers are allocated, so that the D2H copies of the host path land in local memory."""
-    try:
-        import torch
-        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
-        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
-        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
-        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/local_cpulist"
-        cpus = set()
-        for part in open(path).read().strip().split(","):
-            if "-" in part:
-                a, b = part.split("-")
-                cpus.update(range(int(a), int(b) + 1))
-            elif part:
-                cpus.add(int(part))
-        cpus &= set(os.sched_getaffinity(0))
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-            return f"{len(cpus)} cores of the GPU's NUMA node"
-    except Exception as ex:
-        return f"not bound ({type(ex).__name__})"
-    return "not bound"
-
-
 class Timer:
     """max-over-ranks helpers"""
 
@@ -505,7 +480,8 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
-    numa = bind_numa(local) if world > 1 else "single rank: not bound"
+    from mapdn_b200.distributed import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "single rank: not bound"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))

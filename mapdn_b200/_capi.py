@@ -98,17 +98,24 @@ def lib() -> C.CDLL:
     L.mapdn_step_host.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, vp]
     L.mapdn_step_f32obs.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, vp]
     L.mapdn_step_host_f32obs.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, vp]
-    L.mapdn_step_host_pinned.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]
-    L.mapdn_wait.argtypes = [vp, vp]
+    dev_override = bool(os.environ.get("MAPDN_B200_LIB"))       # A/B runs against libraries built from older commits
+    try:
+        L.mapdn_step_host_pinned.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]
+        L.mapdn_wait.argtypes = [vp, vp]
+        L.mapdn_droop.argtypes = [vp, C.c_int32] + [vp] * 5 + [C.c_double, C.c_double, C.c_int32] + [vp] * 5
+    except AttributeError:
+        if not dev_override:
+            raise
     L.mapdn_get_obs.argtypes = [vp, vp, vp]
     L.mapdn_get_state.argtypes = [vp, vp, vp]
     L.mapdn_get_field.argtypes = [vp, C.c_int32, vp, vp]
     L.mapdn_solve.argtypes = [vp, C.c_int32] + [vp] * 11 + [vp]
-    L.mapdn_droop.argtypes = [vp, C.c_int32] + [vp] * 5 + [C.c_double, C.c_double, C.c_int32] + [vp] * 5
     L.mapdn_get_ybus_dense.argtypes = [vp, vp, vp]
     L.mapdn_launch_count.argtypes = [vp]
     L.mapdn_launch_count.restype = C.c_int64
     for name in EXPORTS:
+        if dev_override and not hasattr(L, name):
+            continue
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("mapdn_abi_version",):
             fn.restype = C.c_int32

@@ -21,6 +21,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "kernel_params.h"
 #include "philox.cuh"
 
@@ -125,16 +126,9 @@ template <int G, int NV> __device__ __forceinline__ void grp_reduce(int gidx, in
 __device__ __forceinline__ double fast_rcp(double x) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-#ifdef MAPDN_RCP_TWO_NEWTON
-  double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
-  return fma(r, e, r);
-#else
   const double e = fma(-x, r, 1.0);
   const double t = fma(e, e, e);
   return fma(r, t, r);
-#endif
 }
 
 // sin/cos for the bus angles: distribution-feeder angles are a few degrees, so the common path is a pair of
@@ -244,6 +238,11 @@ struct Hot {
   const double2 *yup, *ydn, *yii;
   const uint64_t *ndesc, *esched, *bsched;
   const uint16_t *lptr, *lidx, *sptr, *sidx, *xptr, *xidx, *node_of_bus;
+  // tables read once per env-step: in the staged blob when it fits the launch shape, else straight from global memory
+  // (generic pointers; the cold copies are prefetched into L2 at kernel start)
+  const double2* ysl;
+  bool in_blob;
+  const unsigned char* blob;          // the staged blob (typed as shared memory at the use sites)
   const uint16_t *nbr_ptr, *nbr_idx;   // meshed nets (dense solver) only
   const double2* nbr_y;
 };
@@ -285,7 +284,7 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
     nd[A_DN] = make_double2(0.0, 0.0);
     nd[A_T] = make_double2(0.0, 0.0);
     nd[A_R] = make_double2(0.0, 0.0);
-    if (i >= npq) { nd[A_D01] = make_double2(sl ? 1.0 : 0.0, 0.0); nd[A_D23] = make_double2(0.0, sl ? 1.0 : 0.0); }
+    if (i >= npq) { nd[A_D01] = make_double2(1.0, 0.0); nd[A_D23] = make_double2(0.0, 1.0); }    // idle lanes eliminate an identity block: no NaN / inf arithmetic
   }
   grp_sync<G>(gidx);
 
@@ -294,54 +293,6 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
   iters = 0;
   const double2 v0 = make_double2(p.e0, p.f0);
   while (true) {
-#ifdef MAPDN_FUSED_MISMATCH
-    PROF(3)
-    // --- one pass per bus: Jacobian terms of the edge (i, parent) in both directions (kept for the sweeps), the terms of
-    //     the edges to the children (recomputed from the children's voltages: cheaper than a second pass + barrier),
-    //     mismatch F = S_calc - S_spec and the diagonal blocks ---
-    double nrm = 0.0;
-#pragma unroll 2
-    for (int i = gl; i < npq; i += G) {
-      const uint64_t ndc = h.ndesc[i];
-      const int pa = static_cast<int>(ndc & 0xFFFFu);             // roots: sentinel record, Y = 0
-      const int c0 = static_cast<int>((ndc >> 16) & 0xFFFFu), c1 = static_cast<int>((ndc >> 32) & 0xFFFFu);
-      const int nx = static_cast<int>((ndc >> 48) & 0x7FFFu);
-      double2* nd = s.node(i);
-      const double2 vi = nd[A_EF], vp = s.node(pa)[A_EF];
-      const double2 w0 = s.node(c0)[A_EF], w1 = s.node(c1)[A_EF];  // no child: sentinel record, Y = 0
-      const double2 yu = h.yup[i], yd = h.ydn[i];
-      const double2 y0 = h.ydn[c0], y1 = h.ydn[c1];                // Y[i, child]
-      const double2 sp = nd[A_SP];
-      const double2 ys = (ndc >> 63) ? __ldg(p.ysl + i) : make_double2(0.0, 0.0);   // Y[i, slack]: slack-adjacent buses only
-      const double2 yi = h.yii[i];
-      const double cc = vi.x * vp.x + vi.y * vp.y;                 // ViVp cos(ti - tp)
-      const double ss = vi.y * vp.x - vi.x * vp.y;                 // ViVp sin(ti - tp)
-      const double2 u = make_double2(yu.x * ss - yu.y * cc, yu.x * cc + yu.y * ss);      // (a, b) of J[i, parent]
-      const double2 d = make_double2(-yd.x * ss - yd.y * cc, yd.x * cc - yd.y * ss);     // (a, b) of J[parent, i]
-      const double k0c = w0.x * vi.x + w0.y * vi.y, k0s = w0.y * vi.x - w0.x * vi.y;     // child 0 seen from i: t_i - t_c
-      const double k1c = w1.x * vi.x + w1.y * vi.y, k1s = w1.y * vi.x - w1.x * vi.y;
-      const double cs0 = vi.x * v0.x + vi.y * v0.y, sn0 = vi.y * v0.x - vi.x * v0.y;
-      double sa = ys.x * sn0 - ys.y * cs0 + u.x + (-y0.x * k0s - y0.y * k0c) + (-y1.x * k1s - y1.y * k1c);
-      double sb = ys.x * cs0 + ys.y * sn0 + u.y + (y0.x * k0c - y0.y * k0s) + (y1.x * k1c - y1.y * k1s);
-      if (p.has_extra_children) {          // warp-uniform: only nets with a bus of degree > 3
-#pragma unroll 1
-        for (int c = c1 + 1; c <= c1 + nx; ++c) {
-          const double2 w = s.node(c)[A_EF], y = h.ydn[c];
-          const double kc = w.x * vi.x + w.y * vi.y, ks = w.y * vi.x - w.x * vi.y;
-          sa += -y.x * ks - y.y * kc; sb += y.x * kc - y.y * ks;
-        }
-      }
-      const double vv = vi.x * vi.x + vi.y * vi.y;
-      const double gv = yi.x * vv, bv = yi.y * vv;
-      const double P = gv + sb, Q = sa - bv;
-      const double Fp = P - sp.x, Fq = Q - sp.y;
-      nd[A_UP] = u; nd[A_DN] = d;
-      nd[A_D01] = make_double2(-Q - bv, P + gv);     // dP/dtheta, dP/dV * V
-      nd[A_D23] = make_double2(P - gv, Q - bv);      // dQ/dtheta, dQ/dV * V
-      nd[A_R] = make_double2(-Fp, -Fq);
-      nrm = nanmax(nrm, nanmax(fabs(Fp), fabs(Fq)));
-    }
-#else
     PROF(2)
     // --- per-edge terms of (i, parent): row i / col parent and row parent / col i ---
 #pragma unroll 4
@@ -368,7 +319,7 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
       const double2 vi = nd[A_EF];
       const double2 u = nd[A_UP], a0 = s.node(c0)[A_DN], a1 = s.node(c1)[A_DN];  // roots: UP = 0; no child: zero slot
       const double2 sp = nd[A_SP];
-      const double2 ys = (ndc >> 63) ? __ldg(p.ysl + i) : make_double2(0.0, 0.0);   // Y[i, slack]: slack-adjacent buses only
+      const double2 ys = (ndc >> 63) ? h.ysl[i] : make_double2(0.0, 0.0);   // Y[i, slack]: slack-adjacent buses only
       const double2 yi = h.yii[i];
       const double cs0 = vi.x * v0.x + vi.y * v0.y, sn0 = vi.y * v0.x - vi.x * v0.y;
       double sa = ys.x * sn0 - ys.y * cs0 + u.x + a0.x + a1.x;
@@ -386,7 +337,6 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
       nd[A_R] = make_double2(-Fp, -Fq);
       nrm = nanmax(nrm, nanmax(fabs(Fp), fabs(Fq)));
     }
-#endif
     {   // ||F||inf < tol for the whole env <=> every thread of the group is below tol (NaN-safe)
       const bool ok = grp_all<G>(gidx, nrm < p.tol);
       if (!done && ok) { done = true; iters = it; }
@@ -470,49 +420,6 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
       grp_sync<G>(gidx);                                 // the last step's results are visible to the back sweep
     }
     PROF(5)
-#ifdef MAPDN_FUSED_UPDATE
-    // --- back substitution root -> leaves, same flat-schedule form (step 0 = the roots: parent = the all-zero
-    //     sentinel, dx = D^-1 r); a lane that solved the parent in the previous step keeps dx_parent in registers.
-    //     The bus's update (theta += dtheta, V += V * dV/V, V = Vm exp(j theta)) is applied right here, off the
-    //     dependent chain; dx itself is stored only when a child will fetch it from shared memory. ---
-    {
-      struct OwnB { double2 m01, m23, x, vv; };
-      auto load_own = [&](uint64_t e) {
-        const double2* nd = s.node(static_cast<int>(e & 0xFFFFu));
-        OwnB o; o.m01 = nd[A_D01]; o.m23 = nd[A_D23]; o.x = nd[A_R]; o.vv = nd[A_VV];
-        return o;
-      };
-      uint64_t bd = h.bsched[gl];
-      uint64_t bd_next = h.bsched[max(0, min(1, p.n_bsteps - 1)) * G + gl];
-      OwnB own = load_own(bd);
-      double2 xl = make_double2(0.0, 0.0);               // dx of the node this lane solved in the previous step
-      for (int st = 0; st < p.n_bsteps; ++st) {
-        const uint64_t bd_next2 = h.bsched[max(0, min(st + 2, p.n_bsteps - 1)) * G + gl];
-        const unsigned bfl = static_cast<unsigned>(bd >> 32);
-        double2* nd = s.node(static_cast<int>(bd & 0xFFFFu));
-        grp_sync<G>(gidx);                                    // the previous step's dx are visible
-        double2 xp = xl;
-        if (!(bfl & kBschedRegParent)) xp = s.node(static_cast<int>((bd >> 16) & 0xFFFFu))[A_R];
-        const OwnB own_next = load_own(bd_next);         // D^-1 J and D^-1 r are final since the forward sweep
-        double2 x = own.x;
-        x.x -= own.m01.x * xp.x + own.m01.y * xp.y;
-        x.y -= own.m23.x * xp.x + own.m23.y * xp.y;
-        xl = x;
-        const bool live = !(bfl & kBschedIdle);          // idle lanes (trash record) store nothing
-        if (live && (bfl & kBschedStoreX)) nd[A_R] = x;
-        {
-          double2 v = own.vv;
-          v.y += x.x;
-          v.x += v.x * x.y;
-          double sn, cs;
-          sincos_angle(v.y, &sn, &cs);
-          if (live && !done) { nd[A_VV] = v; nd[A_EF] = make_double2(v.x * cs, v.x * sn); }
-        }
-        bd = bd_next; bd_next = bd_next2; own = own_next;
-      }
-      grp_sync<G>(gidx);
-    }
-#else
     // --- back substitution root -> leaves, same flat-schedule form (roots: dx = D^-1 r already); a lane
     //     that solved the parent in the previous step keeps dx_parent in registers ---
     {
@@ -561,7 +468,6 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
       }
     }
     grp_sync<G>(gidx);
-#endif
     PROF(6)
   }
   return done;
@@ -596,7 +502,7 @@ __device__ __forceinline__ bool nr_solve_dense(const Params& p, const Hot& h, co
     double nrm = 0.0;
     for (int i = lane; i < npq; i += 32) {
       const double2 vi = s.node(i)[A_EF];
-      const double2 ys = __ldg(p.ysl + i), yi = h.yii[i], sp = s.node(i)[A_SP];
+      const double2 ys = h.ysl[i], yi = h.yii[i], sp = s.node(i)[A_SP];
       const double cs0 = vi.x * v0.x + vi.y * v0.y, sn0 = vi.y * v0.x - vi.x * v0.y;
       double sa = ys.x * sn0 - ys.y * cs0, sb = ys.x * cs0 + ys.y * sn0;
       double* rp = ws + static_cast<size_t>(2 * i) * ld;
@@ -715,6 +621,16 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
   h.xptr = reinterpret_cast<const uint16_t*>(smem_raw + hl.xptr);
   h.xidx = reinterpret_cast<const uint16_t*>(smem_raw + hl.xidx);
   h.node_of_bus = reinterpret_cast<const uint16_t*>(smem_raw + hl.node_of_bus);
+  h.ysl = hl.tables_in_blob ? reinterpret_cast<const double2*>(smem_raw + hl.ysl) : p.ysl;
+  h.in_blob = hl.tables_in_blob != 0;
+  h.blob = smem_raw;
+  if (!hl.tables_in_blob) {      // L2 was possibly flushed: fetch the cold tables now, long before the epilogue needs them
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int k = tid * 128; k < 2 * p.n_sgen * p.obs_dim; k += nt * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.obs_off) + k));
+    for (int k = tid * 128; k < 4 * p.n_line; k += nt * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.line_nodes) + k));
+    for (int k = tid * 128; k < 32 * p.n_line; k += nt * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.line_c) + k));
+    for (int k = tid * 128; k < 16 * p.npq; k += nt * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.ysl) + k));
+  }
   h.nbr_ptr = reinterpret_cast<const uint16_t*>(smem_raw + hl.nbr_ptr);
   h.nbr_idx = reinterpret_cast<const uint16_t*>(smem_raw + hl.nbr_idx);
   h.nbr_y = reinterpret_cast<const double2*>(smem_raw + hl.nbr_y);
@@ -746,9 +662,6 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
   double* red_scratch = s.scratch + ng;
   const bool stage_rec = p.stage_in_records != 0;
   double* stage_lin = s.scratch + ng + (G > 32 ? 10 * (G / 32) : 0);
-  auto stage = [&](int k) -> double* {
-    return stage_rec ? s.base + (k / 12) * (2 * kNodeArrays2) + 2 * A_UP + (k % 12) : stage_lin + k;
-  };
   const uint32_t k0 = static_cast<uint32_t>(p.seed), k1 = static_cast<uint32_t>(p.seed >> 32);
 
   for (int base = blockIdx.x * epb; base < p.nb; base += gridDim.x * epb) {
@@ -801,14 +714,21 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
             sd[u][k] = ok[u] ? __ldg(sds + j) : 0.0;
           }
         }
-#pragma unroll
+        // one copy of Philox + log + sqrt + sincos (not four: the solver warps need the instruction cache); the work
+        // item is picked out of the registers with select chains
+#pragma unroll 1
         for (int u = 0; u < U; ++u) {
-          if (!ok[u]) continue;
-          const int e = e_[u], m = m_[u], env_h = base + e;
+          bool oku = ok[0]; int e = e_[0], m = m_[0];
+          double va = val[0][0], vb = val[0][1], sa = sd[0][0], sb = sd[0][1];
+#pragma unroll
+          for (int q = 1; q < U; ++q)
+            if (u == q) { oku = ok[q]; e = e_[q]; m = m_[q]; va = val[q][0]; vb = val[q][1]; sa = sd[q][0]; sb = sd[q][1]; }
+          if (!oku) continue;
+          const int env_h = base + e;
           const int4 sc = hs[e];
           RngKey key_h{k0, k1, static_cast<uint32_t>(p.env_id_offset + env_h), static_cast<uint32_t>(sc.w) * 8u};
-          double z[2] = {0.0, 0.0};
-          if (p.add_noise) half_normal_pair(key_h, static_cast<uint32_t>(sc.z), m, z[0], z[1]);
+          double z0 = 0.0, z1 = 0.0;
+          if (p.add_noise) half_normal_pair(key_h, static_cast<uint32_t>(sc.z), m, z0, z1);
           double* pv_next = reinterpret_cast<double*>(reinterpret_cast<double2*>(smem_raw + hl_bytes) +
                                                        static_cast<size_t>(e) * p.env_stride2 + p.scratch_off2);
           const size_t hL = static_cast<size_t>(env_h) * nl, hG = static_cast<size_t>(env_h) * ng;
@@ -816,7 +736,7 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
           for (int k = 0; k < 2; ++k) {
             const int el = 2 * m + k;
             if (el >= n_elem) break;
-            const double v = val[u][k] + sd[u][k] * z[k];
+            const double v = (k == 0) ? va + sa * z0 : vb + sb * z1;
             const bool is_pv = el < ng, is_lp = el < ng + nl;
             double* dst = is_pv ? p.cur_pv + hG + el : (is_lp ? p.cur_pl + hL + (el - ng) : p.cur_ql + hL + (el - ng - nl));
             *dst = v;
@@ -899,38 +819,44 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
       }
       }
       // (droop re-stages the loads every round: the staging area is overwritten by the Newton iteration)
+      // Written once, instantiated for the two staging places (block-uniform choice): a branch per access inside the
+      // loops cost 0.7 us per step on case33.
+      auto stage_and_gather = [&](auto stg) {
 #pragma unroll 4
-      for (int l = gl; l < nl; l += G) {
-        double pl, ql;
-        if (MODE == MODE_SOLVE || MODE == MODE_DROOP) { pl = p.in_pl[eL + l]; ql = p.in_ql[eL + l]; }
-        else if (MODE == MODE_STEP) { pl = p.cur_pl[eL + l]; ql = p.cur_ql[eL + l]; }
-        else {
-          pl = __ldg(p.prof_lp + row * nl + l);
-          ql = __ldg(p.prof_lq + row * nl + l);
-          if (p.add_noise) {                                                   // :503, :508
-            pl += __ldg(p.lp_std + l) * half_normal(key, c1, ng + l);
-            ql += __ldg(p.lq_std + l) * half_normal(key, c1, ng + nl + l);
+        for (int l = gl; l < nl; l += G) {
+          double pl, ql;
+          if (MODE == MODE_SOLVE || MODE == MODE_DROOP) { pl = p.in_pl[eL + l]; ql = p.in_ql[eL + l]; }
+          else if (MODE == MODE_STEP) { pl = p.cur_pl[eL + l]; ql = p.cur_ql[eL + l]; }
+          else {
+            pl = __ldg(p.prof_lp + row * nl + l);
+            ql = __ldg(p.prof_lq + row * nl + l);
+            if (p.add_noise) {                                                   // :503, :508
+              pl += __ldg(p.lp_std + l) * half_normal(key, c1, ng + l);
+              ql += __ldg(p.lq_std + l) * half_normal(key, c1, ng + nl + l);
+            }
+            if (valid) { p.cur_pl[eL + l] = pl; p.cur_ql[eL + l] = ql; }
           }
-          if (valid) { p.cur_pl[eL + l] = pl; p.cur_ql[eL + l] = ql; }
+          const double sc = __ldg(p.lscale + l);
+          *stg(l) = pl * sc; *stg(nl + l) = ql * sc;
         }
-        const double sc = __ldg(p.lscale + l);
-        *stage(l) = pl * sc; *stage(nl + l) = ql * sc;
-      }
-      if (!hot_ready) { stage_hot_wait(&stage_bar); hot_ready = true; }
-      grp_sync<G>(gidx);
-      // (2) A.1: PD/QD per bus, Sbus = -(PD + jQD)/baseMVA
-      for (int i = gl; i < npq; i += G) {
-        double pd = 0.0, qd = 0.0;
+        if (!hot_ready) { stage_hot_wait(&stage_bar); hot_ready = true; }
+        grp_sync<G>(gidx);
+        // (2) A.1: PD/QD per bus, Sbus = -(PD + jQD)/baseMVA
+        for (int i = gl; i < npq; i += G) {
+          double pd = 0.0, qd = 0.0;
 #pragma unroll 1
-        for (int t = h.lptr[i], te = h.lptr[i + 1]; t < te; ++t) { const int l = h.lidx[t]; pd += *stage(l); qd += *stage(nl + l); }
+          for (int t = h.lptr[i], te = h.lptr[i + 1]; t < te; ++t) { const int l = h.lidx[t]; pd += *stg(l); qd += *stg(nl + l); }
 #pragma unroll 1
-        for (int t = h.sptr[i], te = h.sptr[i + 1]; t < te; ++t) {
-          const int g = h.sidx[t];
-          const double sc = __ldg(p.sscale + g);
-          pd -= s.pv[g] * sc; qd -= s.q[g] * sc;
+          for (int t = h.sptr[i], te = h.sptr[i + 1]; t < te; ++t) {
+            const int g = h.sidx[t];
+            const double sc = __ldg(p.sscale + g);
+            pd -= s.pv[g] * sc; qd -= s.q[g] * sc;
+          }
+          s.node(i)[A_SP] = make_double2(-pd * p.inv_base, -qd * p.inv_base);
         }
-        s.node(i)[A_SP] = make_double2(-pd * p.inv_base, -qd * p.inv_base);
-      }
+      };
+      if (stage_rec) stage_and_gather([&](int k) -> double* { return s.base + (k / 12) * (2 * kNodeArrays2) + 2 * A_UP + (k % 12); });
+      else stage_and_gather([&](int k) -> double* { return stage_lin + k; });
       grp_sync<G>(gidx);
       if (MODE == MODE_STEP) named_bar_arrive(1, blockDim.x);   // the current rows are consumed: the helper may overwrite them
 
@@ -1082,22 +1008,26 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
         }
       }
     }
-    // line losses: res_line.pl_mw = Re(Sf + St), 4 static coefficients per line
+    // line losses: res_line.pl_mw = Re(Sf + St), 4 static coefficients per line. The two tables are either
+    // part of the staged blob (LDS) or cold in global memory (read-only path): one block-uniform branch, two typed loops.
     double sum_pl = 0.0;
     {
       const size_t ePL = static_cast<size_t>(env) * p.n_line;
+      auto lines = [&](const ushort2* __restrict__ ln, const double2* __restrict__ lc) {
 #pragma unroll 4
-      for (int k = gl; k < p.n_line; k += G) {
-        const ushort2 ft = __ldg(reinterpret_cast<const ushort2*>(p.line_nodes) + k);     // cold tables: once per env-step, coalesced
-        const double2 vf = s.node(ft.x)[A_EF], vt = s.node(ft.y)[A_EF];
-        const double cc = vf.x * vt.x + vf.y * vt.y, ss = vf.y * vt.x - vf.x * vt.y;
-        const double2 c01 = __ldg(reinterpret_cast<const double2*>(p.line_c) + 2 * k);
-        const double2 c23 = __ldg(reinterpret_cast<const double2*>(p.line_c) + 2 * k + 1);
-        const double pl = c01.x * (vf.x * vf.x + vf.y * vf.y) + c01.y * (vt.x * vt.x + vt.y * vt.y) + c23.x * cc + c23.y * ss;
-        sum_pl += pl;
-        if (kExplicit) { if (valid && p.out_pl) p.out_pl[ePL + k] = pl; }
-        else if (write_res) p.res_pl[ePL + k] = pl;
-      }
+        for (int k = gl; k < p.n_line; k += G) {
+          const ushort2 ft = ln[k];
+          const double2 vf = s.node(ft.x)[A_EF], vt = s.node(ft.y)[A_EF];
+          const double cc = vf.x * vt.x + vf.y * vt.y, ss = vf.y * vt.x - vf.x * vt.y;
+          const double2 c01 = lc[2 * k], c23 = lc[2 * k + 1];
+          const double pl = c01.x * (vf.x * vf.x + vf.y * vf.y) + c01.y * (vt.x * vt.x + vt.y * vt.y) + c23.x * cc + c23.y * ss;
+          sum_pl += pl;
+          if (kExplicit) { if (valid && p.out_pl) p.out_pl[ePL + k] = pl; }
+          else if (write_res) p.res_pl[ePL + k] = pl;
+        }
+      };
+      if (h.in_blob) lines(reinterpret_cast<const ushort2*>(smem_raw + hl.line_nodes), reinterpret_cast<const double2*>(smem_raw + hl.line_c));
+      else lines(reinterpret_cast<const ushort2*>(p.line_nodes), reinterpret_cast<const double2*>(p.line_c));
     }
     PROF(9)
     if (kExplicit) {
@@ -1140,12 +1070,19 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
         p.term[env] = (steps_new >= p.episode_limit || !conv) ? 1 : 0;          // :204
         p.steps[env] = steps_new;
         p.sum_rewards[env] += reward;                                           // :203
-        if (p.info) {
-          double* o = p.info + static_cast<size_t>(env) * 11;
-          o[0] = pct; o[1] = cnt_lo * inv_n; o[2] = cnt_hi * inv_n;
-          o[3] = (!conv || pct > 1e-3) ? 0.0 : 1.0;                             // :589, :195
-          o[4] = sum_dev * inv_n; o[5] = sum_v * inv_n; o[6] = max_drop; o[7] = max_rise;
-          o[8] = sum_pl; o[9] = conv ? q_loss : sum_q_try / ng; o[10] = conv ? 0.0 : 1.0;
+      }
+      if (valid && p.info != nullptr) {
+        // the 11 info scalars, one per lane (every lane of the group holds the reduced values): one or two store
+        // instructions per env instead of eleven from lane 0 - it matters when `info` is pinned host memory
+        double* o = p.info + static_cast<size_t>(env) * 11;
+        const double i3 = (!conv || pct > 1e-3) ? 0.0 : 1.0;                     // :589, :195
+        const double i9 = conv ? q_loss : sum_q_try / ng, i10 = conv ? 0.0 : 1.0;
+        for (int k = gl; k < 11; k += G) {
+          double v = pct;                                                         // select chain, no divergent branches
+          v = (k == 1) ? cnt_lo * inv_n : v; v = (k == 2) ? cnt_hi * inv_n : v; v = (k == 3) ? i3 : v;
+          v = (k == 4) ? sum_dev * inv_n : v; v = (k == 5) ? sum_v * inv_n : v; v = (k == 6) ? max_drop : v;
+          v = (k == 7) ? max_rise : v; v = (k == 8) ? sum_pl : v; v = (k == 9) ? i9 : v; v = (k == 10) ? i10 : v;
+          o[k] = v;
         }
       }
     } else {  // MODE_RESET
@@ -1158,24 +1095,64 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
       }
     }
     PROF(10)
-    // observations of the new state (reference get_obs :232-316): a pure gather - the program maps
-    // every entry to a double inside this env's slab (or to a constant-zero slot for the padding)
-    if (p.obs != nullptr && valid) {
-      double* o = p.obs + static_cast<size_t>(env) * ng * p.obs_dim;
+    // observations of the new state (reference get_obs :232-316): a pure gather - the program maps every entry to a
+    // double inside this env's slab, or to a constant-zero slot for the padding. A lane copies 16 bytes per
+    // instruction (two fp64 / four fp32 entries) and consecutive lanes consecutive 16-byte pieces, so one store
+    // instruction writes 128 contiguous bytes per env (full lines when the destination is pinned host memory).
+    // obs_skip_off: entries reading that slot (the padding) are not stored.
+    if ((p.obs != nullptr || (MODE == MODE_STEP && p.obs32 != nullptr)) && valid) {
       const int tot = ng * p.obs_dim;
-#pragma unroll 4
-      for (int idx = gl; idx < tot; idx += G) {
-        const int off = __ldg(p.obs_off + idx);
-        if (off != p.obs_skip_off) o[idx] = s.base[off];      // obs_skip_off = the zero slot when the padding is not rewritten
-      }
-    } else if (MODE == MODE_STEP && p.obs32 != nullptr && valid) {
-      float* o = p.obs32 + static_cast<size_t>(env) * ng * p.obs_dim;
-      const int tot = ng * p.obs_dim;
-#pragma unroll 4
-      for (int idx = gl; idx < tot; idx += G) {
-        const int off = __ldg(p.obs_off + idx);
-        if (off != p.obs_skip_off) o[idx] = static_cast<float>(s.base[off]);
-      }
+      const int skip = p.obs_skip_off;
+      auto gather = [&](const uint16_t* __restrict__ prog, auto cold) {   // prog: shared (blob) or global (cold copy: read-only path)
+        constexpr bool kCold = decltype(cold)::value;
+        int done_to = 0;
+        if (p.obs != nullptr) {
+          double* o = p.obs + static_cast<size_t>(env) * tot;
+          if ((tot & 1) == 0 && (reinterpret_cast<uintptr_t>(p.obs) & 15) == 0) {
+            const uint32_t* offv = reinterpret_cast<const uint32_t*>(prog);
+            const int npair = tot >> 1;
+#pragma unroll (kCold ? 8 : 4)
+            for (int c = gl; c < npair; c += G) {
+              const uint32_t w = kCold ? __ldg(offv + c) : offv[c];
+              const int o0 = static_cast<int>(w & 0xFFFFu), o1 = static_cast<int>(w >> 16);
+              const double v0 = s.base[o0], v1 = s.base[o1];
+              if (o0 != skip && o1 != skip) *reinterpret_cast<double2*>(o + 2 * c) = make_double2(v0, v1);
+              else { if (o0 != skip) o[2 * c] = v0; if (o1 != skip) o[2 * c + 1] = v1; }
+            }
+            done_to = tot;
+          }
+          for (int idx = done_to + gl; idx < tot; idx += G) {
+            const int off = prog[idx];
+            if (off != skip) o[idx] = s.base[off];
+          }
+        } else {
+          float* o = p.obs32 + static_cast<size_t>(env) * tot;
+          if ((tot & 3) == 0 && (reinterpret_cast<uintptr_t>(p.obs32) & 15) == 0) {
+            const uint2* offv = reinterpret_cast<const uint2*>(prog);
+            const int nquad = tot >> 2;
+#pragma unroll (kCold ? 8 : 4)
+            for (int c = gl; c < nquad; c += G) {
+              const uint2 w = kCold ? __ldg(offv + c) : offv[c];
+              const int o0 = static_cast<int>(w.x & 0xFFFFu), o1 = static_cast<int>(w.x >> 16);
+              const int o2 = static_cast<int>(w.y & 0xFFFFu), o3 = static_cast<int>(w.y >> 16);
+              const float v0 = static_cast<float>(s.base[o0]), v1 = static_cast<float>(s.base[o1]);
+              const float v2 = static_cast<float>(s.base[o2]), v3 = static_cast<float>(s.base[o3]);
+              if (o0 != skip && o1 != skip && o2 != skip && o3 != skip) *reinterpret_cast<float4*>(o + 4 * c) = make_float4(v0, v1, v2, v3);
+              else {
+                if (o0 != skip) o[4 * c] = v0; if (o1 != skip) o[4 * c + 1] = v1;
+                if (o2 != skip) o[4 * c + 2] = v2; if (o3 != skip) o[4 * c + 3] = v3;
+              }
+            }
+            done_to = tot;
+          }
+          for (int idx = done_to + gl; idx < tot; idx += G) {
+            const int off = prog[idx];
+            if (off != skip) o[idx] = static_cast<float>(s.base[off]);
+          }
+        }
+      };
+      if (h.in_blob) gather(reinterpret_cast<const uint16_t*>(smem_raw + hl.obs_off), std::false_type{});
+      else gather(p.obs_off, std::true_type{});
     }
     if (MODE == MODE_RESET && p.state != nullptr) {
       // get_state (:213-230): [P_bus | Q_bus | pv | q | vm | va(deg)] restricted to state_space (cold program)

@@ -36,16 +36,20 @@ constexpr unsigned kEschedStore = 0x800u;   // the parent will read this bus's S
 // bsched flags (bits 32.. of an entry)
 constexpr unsigned kBschedRegParent = 0x1u; // dx of the parent is in this lane's registers (it solved the parent in the previous step)
 constexpr unsigned kBschedIdle = 0x2u;      // idle lane of this step (trash record)
-constexpr unsigned kBschedStoreX = 0x4u;    // a child will fetch this bus's dx from shared memory
 
 struct HotLayout {        // byte offsets inside the hot static blob (staged into smem per CTA)
   int yup, ydn;           // double2 [npq], [npq + 1]: Y[i,parent], Y[parent,i]   (G, B); ydn[npq] = 0 ("no child")
   int yii;                // double2 [npq]: Y[i,i]
+  int tables_in_blob;     // the four once-per-step tables below are part of the blob (else: the cold copies in Params)
+  int ysl;                // double2 [npq]: Y[i,slack]
+  int obs_off;            // uint16 [n_sgen*obs_dim]: obs entry -> double offset inside the env slab
+  int line_nodes;         // uint16 [2*n_line]: from / to node of every line (npq = slack)
+  int line_c;             // double [4*n_line]: loss coefficients (see mapdn_b200.cu)
   int ndesc;              // uint64 [npq]: node descriptor, see below
   int esched;             // uint64 [n_esteps * G]: elimination schedule, one entry per (step, lane):
                           //   node | child0<<16 | child1<<32 | flags<<48   (idle lane: trash record)
   int bsched;             // uint64 [n_bsteps * G]: back-substitution schedule: node | parent<<16 | kBsched* flags<<32
-                          //   (step 0 = the roots, parent = the all-zero sentinel record)
+                          //   (levels 1.. of the forest: the roots' dx = D^-1 r is already in place)
   int lptr, lidx;         // uint16 [npq+2], [n_load]: node -> loads (CSR); node npq = slack bus
   int sptr, sidx;         // uint16 [npq+2], [n_sgen]: node -> sgens
   int xptr, xidx;         // uint16 [npq+2], [<=n_sgen]: node -> sgens of the node's own zone (obs add-back)
@@ -79,7 +83,7 @@ struct Params {
   const int* bus_of_node;                                     // [npq]
   const double* lscale; const double* sscale;                 // scaling by load id / sgen id
   const int* sl_node; const double* sl_y;                     // slack-adjacent nodes, Y[slack,i] (G,B)
-  // cold tables read once per env-step (coalesced, read-only path) - kept out of the shared-memory blob
+  // cold copies of the once-per-step tables (used when they are left out of the shared-memory blob: large nets)
   const double2* ysl;                                         // [npq] Y[i,slack] (zero unless adjacent to the slack)
   const uint16_t* obs_off;                                    // [n_sgen*obs_dim] obs entry -> double offset in the env slab
   const uint16_t* line_nodes;                                 // [2*n_line] from / to node of every line (npq = slack)

@@ -203,10 +203,7 @@ std::vector<T> vec_or(const T* p, size_t n, T fill) {
 }
 
 using KernelFn = void (*)(const Params);
-#ifndef MAPDN_HELPER_PAIRS_PER_WARP
-#define MAPDN_HELPER_PAIRS_PER_WARP 256
-#endif
-constexpr int kHelperPairsPerWarp = MAPDN_HELPER_PAIRS_PER_WARP;   // Box-Muller pairs of a CTA round per helper warp
+constexpr int kHelperPairsPerWarp = 256;   // Box-Muller pairs of a CTA round per helper warp (1024 measured slower: +2 us on case33)
 
 template <int G>
 KernelFn kernel_for_mode(int mode) {
@@ -246,12 +243,12 @@ bool stage_fits_records(int npq, int nl) { return 2 * nl <= 12 * (npq + 2); }
 
 // scratch doubles per env: next pv row / droop voltages [n_sgen], the partial sums per warp of the multi-warp group
 // reductions, and the staged loads when they do not fit the records
-int scratch_doubles_for(int npq, int ng, int nl, int G) {
-  return ng + (G > 32 ? 10 * (G / 32) : 0) + (stage_fits_records(npq, nl) ? 0 : 2 * nl);
+int scratch_doubles_for(int ng, int nl, int G, bool stage_rec) {
+  return ng + (G > 32 ? 10 * (G / 32) : 0) + (stage_rec ? 0 : 2 * nl);
 }
 
-int env_stride2_for(int npq, int ng, int nl, int G) {
-  int stride = kNodeArrays2 * (npq + 2) + ng + (scratch_doubles_for(npq, ng, nl, G) + 1) / 2;
+int env_stride2_for(int npq, int ng, int nl, int G, bool stage_rec) {
+  int stride = kNodeArrays2 * (npq + 2) + ng + (scratch_doubles_for(ng, nl, G, stage_rec) + 1) / 2;
   if (G == 4) while ((stride * 16) % 128 != 64) ++stride;
   return stride;
 }
@@ -486,7 +483,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   for (int l = 0; l < n_lev; ++l) max_width = std::max(max_width, elev[l + 1] - elev[l]);
   for (int i = 0; i < npq; ++i) max_children = std::max(max_children, nchild[i]);
   int G = cfg->lanes_per_env;
-  if (G == 0) G = (npq <= 64) ? 8 : 32;
+  if (G == 0) G = (npq <= 64) ? 8 : (npq <= 256 ? 32 : 64);      // measured on B200 (profiles/r02_sweeps.txt)
   if (meshed) G = 32;                    // the dense fallback works one warp per env     // measured on B200: 8 lanes/env for 33-bus feeders, a full warp beyond
   // Flat schedules for this G: a level wider than G takes several steps; idle lanes get the trash record.
   // Lanes follow chains: a bus is placed on the lane that handled its child (forward sweep) / its parent
@@ -535,18 +532,10 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     // a bus stores its Schur update only if its parent will fetch it from shared memory
     for (int i = 0; i < npq; ++i)
       if (parent[i] >= 0 && reg_child[parent[i]] != i) esched[epos[i]] |= static_cast<uint64_t>(kEschedStore) << 48;
-    // back sweep by depth (step 0 = the roots, whose "parent" is the all-zero sentinel record): children inherit the
-    // lane of their parent (the child with the tallest subtree first). The sweep also applies the Newton update to
-    // the bus it solves, so every bus appears exactly once.
+    // back sweep by depth: children inherit the lane of their parent (the child with the tallest subtree first)
     std::fill(lane_of.begin(), lane_of.end(), -1); std::fill(step_of.begin(), step_of.end(), -1);
-    std::vector<int> bpos(npq, -1);
-    std::vector<char> regp(npq, 0);
     cur = 0;
-#ifdef MAPDN_FUSED_UPDATE
-    const int first_back_level = 0;
-#else
     const int first_back_level = 1;      // the roots' dx = D^-1 r is already in place
-#endif
     for (int l = first_back_level; l < n_lev; ++l) {
       const int w = dlev[l + 1] - dlev[l], nst = (w + G - 1) / G;
       std::vector<int> slot(static_cast<size_t>(nst) * G, -1);
@@ -570,23 +559,17 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
           continue;
         }
         lane_of[i] = sidx % G; step_of[i] = cur + sidx / G;
-        regp[i] = reg[i] && sidx / G == 0;
-        bpos[i] = static_cast<int>(bsched.size());
         bsched.push_back(static_cast<uint64_t>(i) | (static_cast<uint64_t>(parent[i] >= 0 ? parent[i] : npq) << 16) |
-                         (static_cast<uint64_t>(regp[i] ? kBschedRegParent : 0u) << 32));
+                         (static_cast<uint64_t>((reg[i] && sidx / G == 0) ? kBschedRegParent : 0u) << 32));
       }
       cur += nst;
     }
-    // a bus stores its dx only if a child will fetch it from shared memory (roots: D^-1 r is already in place)
-    for (int i = 0; i < npq; ++i)
-      if (parent[i] >= 0 && !regp[i] && parent[parent[i]] >= 0) bsched[bpos[parent[i]]] |= static_cast<uint64_t>(kBschedStoreX) << 32;
   }
   if (getenv("MAPDN_DEBUG_SCHED")) {
     int nreg = 0, nl0 = 0, nl1 = 0, nreal = 0;
     for (uint64_t e2 : esched) { if ((e2 & 0xFFFF) == (uint64_t)trash) continue; ++nreal; unsigned fl = e2 >> 48; nreg += !!(fl & kEschedReg0); nl0 += !!(fl & kEschedLoad0); nl1 += !!(fl & kEschedLoad1); }
     int breg = 0, breal = 0;
     for (uint64_t b2 : bsched) { if ((b2 & 0xFFFF) == (uint64_t)trash) continue; ++breal; breg += (b2 >> 32) & 1; }
-    { int nsx = 0; for (uint64_t b2 : bsched) nsx += ((b2 >> 32) & kBschedStoreX) ? 1 : 0; fprintf(stderr, "[sched] back sweep: %d buses store dx\n", nsx); }
     fprintf(stderr, "[sched] G=%d levels=%d esteps=%zu real=%d reg0=%d load0=%d load1=%d | bsteps=%zu real=%d regp=%d\n", G, n_lev,
             esched.size() / G, nreal, nreg, nl0, nl1, bsched.size() / G, breal, breg);
   }
@@ -628,7 +611,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     obs_dim = std::max(obs_dim, nz * (2 * ss_dem + ss_vm + ss_va) + ss_pv + ss_q);
   }
   const int pvq_off2 = kNodeArrays2 * na, scratch_off2 = pvq_off2 + ng;
-  if (2 * (scratch_off2 + (scratch_doubles_for(npq, ng, nl, G) + 1) / 2) >= 65535)
+  if (2 * (scratch_off2 + (scratch_doubles_for(ng, nl, G, false) + 1) / 2) >= 65535)
     return bail(fail(MAPDN_ERR_UNSUPPORTED, "network too large for 16-bit slab offsets"));
   std::vector<uint16_t> obs_off(static_cast<size_t>(ng) * obs_dim);
   std::vector<unsigned> obs_src(static_cast<size_t>(ng) * obs_dim, 0u);
@@ -706,6 +689,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   }
   // ---- 3b. hot static blob ----
   HotLayout hl{};
+  int bytes_core = 0, bytes_full = 0;
   {
     int off = 0;
     auto take = [&](size_t bytes) { int o = off; off += static_cast<int>((bytes + 15) / 16 * 16); return o; };
@@ -717,9 +701,15 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     hl.node_of_bus = take(2 * n);
     hl.nbr_ptr = take(2 * nbr_ptr.size()); hl.nbr_idx = take(2 * std::max<size_t>(1, nbr_idx.size()));
     hl.nbr_y = take(8 * std::max<size_t>(2, nbr_y.size()));
-    hl.bytes = off;
+    bytes_core = off;
+    // the once-per-step tables go last: the TMA copy either includes them (hl.bytes = bytes_full) or stops before them
+    if (line_nodes.empty()) { line_nodes.assign(2, 0); line_c.assign(4, 0.0); }
+    hl.ysl = take(16 * npq); hl.obs_off = take(2 * obs_off.size());
+    hl.line_nodes = take(2 * line_nodes.size()); hl.line_c = take(8 * line_c.size());
+    bytes_full = off;
+    hl.bytes = bytes_full; hl.tables_in_blob = 1;
   }
-  std::vector<unsigned char> hot(hl.bytes, 0);
+  std::vector<unsigned char> hot(bytes_full, 0);
   std::vector<double> ysl_cold(2 * static_cast<size_t>(npq), 0.0);     // Y[i,slack]: cold table, non-zero for a few buses
   std::vector<int> sl_node;
   std::vector<double> sl_y;
@@ -756,6 +746,10 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     std::memcpy(hot.data() + hl.sidx, sidx.data(), 2 * sidx.size());
     std::memcpy(hot.data() + hl.xptr, xptr.data(), 2 * xptr.size());
     if (!xidx.empty()) std::memcpy(hot.data() + hl.xidx, xidx.data(), 2 * xidx.size());
+    std::memcpy(hot.data() + hl.ysl, ysl_cold.data(), 8 * ysl_cold.size());
+    std::memcpy(hot.data() + hl.obs_off, obs_off.data(), 2 * obs_off.size());
+    std::memcpy(hot.data() + hl.line_nodes, line_nodes.data(), 2 * line_nodes.size());
+    std::memcpy(hot.data() + hl.line_c, line_c.data(), 8 * line_c.size());
     uint16_t* nob = reinterpret_cast<uint16_t*>(hot.data() + hl.node_of_bus);
     for (int b = 0; b < n; ++b) nob[b] = static_cast<uint16_t>(node_of_bus[b]);
     std::memcpy(hot.data() + hl.nbr_ptr, nbr_ptr.data(), 2 * nbr_ptr.size());
@@ -768,33 +762,64 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   // ---- 5. launch geometry ----
   cudaDeviceProp dp{};
   TRY_CUDA(cudaGetDeviceProperties(&dp, device));
-  const int stride2 = env_stride2_for(npq, ng, nl, G);
   const size_t max_smem = dp.sharedMemPerBlockOptin;
   // envs per CTA: sub-warp groups pack 32/G envs into each of 1..4 solver warps; multi-warp groups (G = 64 / 128)
   // put 1..4 envs of G threads in a CTA. Fewer envs per CTA when that spreads the batch over all SMs.
-  auto smem_for = [&](int epb) { return static_cast<size_t>(hl.bytes) + static_cast<size_t>(epb) * (stride2 * 16 + 16); };   // + helper scalars
   const int unit = (G <= 32) ? 32 / G : 1;               // envs added per step of the search
-  // measured on B200 (profiles/): two solver warps per CTA for small sub-warp groups, four for one-warp envs,
-  // as many multi-warp envs as fit (<= 512 solver threads)
-  int epb = (G <= 16) ? 2 * unit : 4 * unit;
-  if (G > 32) while (epb > 1 && epb * G > 512) --epb;
-  // Few-round batches (the BASELINE.json configs): one CTA per SM holding ceil(B / (SMs * rounds)) envs balances the
-  // SMs exactly (case33 x 4096: 147 CTAs of 28 envs instead of 512 of 8, i.e. 7 instead of up to 8 solver warps on
-  // the busiest SM; case141 x 2048: 2 rounds of 7). Many-round batches keep several small CTAs per SM.
-  {
-    auto fits = [&](int c) { return smem_for(c) <= max_smem && c * G <= (G <= 32 ? 256 : 512); };
-    const int n_sm = dp.multiProcessorCount;
+  const int n_sm = dp.multiProcessorCount;
+  int stride2 = 0, epb = 0;
+  bool stage_rec = false;
+  // Two ways to buy shared memory when it limits the envs per SM, both with a price (measured, profiles/): (a) the four
+  // once-per-step tables (Y[i,slack], obs program, line tables) stay in global memory instead of the staged blob - their
+  // first touch after an L2 flush is an HBM round trip at the start of the epilogue, softened by an L2 prefetch at kernel
+  // start; (b) the prologue stages the scaled loads inside the node records - index arithmetic, +1.3 k cycles per step on
+  // case33. Each is used only if it lets the batch finish in fewer rounds (case322 x 1024: 4 envs per SM and 2 rounds
+  // instead of 3 and 3).
+  struct Plan { bool cold, rec, ok; int st2, epb; long long rounds; };
+  auto smem_with = [&](bool cold, int st2, int c) {
+    return static_cast<size_t>(cold ? bytes_core : bytes_full) + static_cast<size_t>(c) * (st2 * 16 + 16);   // + helper scalars
+  };
+  auto make_plan = [&](bool cold, bool rec) {
+    Plan pl{cold, rec, false, 0, 0, 0};
+    if (rec && !stage_fits_records(npq, nl)) return pl;
+    pl.st2 = env_stride2_for(npq, ng, nl, G, rec);
+    // measured on B200 (profiles/): two solver warps per CTA for small sub-warp groups, four for one-warp envs,
+    // as many multi-warp envs as fit (<= 512 solver threads)
+    int c_epb = (G <= 16) ? 2 * unit : 4 * unit;
+    if (G > 32) while (c_epb > 1 && c_epb * G > 512) --c_epb;
+    // Few-round batches (the BASELINE.json configs): one CTA per SM holding ceil(B / (SMs * rounds)) envs balances the
+    // SMs exactly (case33 x 4096: 147 CTAs of 28 envs instead of 512 of 8, i.e. 7 instead of up to 8 solver warps on
+    // the busiest SM; case141 x 2048: 2 rounds of 7). Many-round batches keep several small CTAs per SM.
+    auto fits = [&](int c) { return smem_with(cold, pl.st2, c) <= max_smem && c * G <= (G <= 32 ? 256 : 512); };
     for (int r = 1; r <= 3; ++r) {
       int c = (cfg->batch + n_sm * r - 1) / (n_sm * r);
       c = (c + unit - 1) / unit * unit;
-      if (fits(c)) { epb = std::max(epb, c); break; }
+      if (fits(c)) { c_epb = std::max(c_epb, c); break; }
     }
+    if (const char* ov = getenv("MAPDN_EPB")) c_epb = std::max(unit, atoi(ov) / unit * unit);   // tuning override
+    while (c_epb > unit && (smem_with(cold, pl.st2, c_epb) > max_smem || (G <= 32 && c_epb * G > 256))) c_epb -= unit;
+    pl.epb = c_epb;
+    pl.ok = smem_with(cold, pl.st2, c_epb) <= max_smem;
+    pl.rounds = (cfg->batch + static_cast<long long>(c_epb) * n_sm - 1) / (static_cast<long long>(c_epb) * n_sm);
+    return pl;
+  };
+  bool cold_tables = false;
+  {
+    const Plan plans[4] = {make_plan(false, false), make_plan(false, true), make_plan(true, false), make_plan(true, true)};   // cheapest first
+    const Plan* best = nullptr;
+    for (const Plan& pl : plans) if (pl.ok && (!best || pl.rounds < best->rounds)) best = &pl;
+    if (const char* ov = getenv("MAPDN_PLAN")) {             // tuning override: 0..3 = index into the list above
+      const int k = atoi(ov);
+      if (k >= 0 && k < 4 && plans[k].ok) best = &plans[k];
+    }
+    if (best) { stride2 = best->st2; epb = best->epb; stage_rec = best->rec; cold_tables = best->cold; }
   }
-  if (const char* ov = getenv("MAPDN_EPB")) epb = std::max(unit, atoi(ov) / unit * unit);   // tuning override
-  while (epb > unit && (smem_for(epb) > max_smem || (G <= 32 && epb * G > 256))) epb -= unit;
-  if (smem_for(epb) > max_smem)
+  hl.tables_in_blob = cold_tables ? 0 : 1;
+  hl.bytes = cold_tables ? bytes_core : bytes_full;
+  auto smem_for = [&](int c) { return smem_with(cold_tables, stride2, c); };
+  if (epb == 0 || smem_for(epb) > max_smem)
     return bail(fail(MAPDN_ERR_UNSUPPORTED, "network too large for the shared-memory resident solver (" +
-                                                std::to_string(smem_for(epb)) + " B needed)"));
+                                                std::to_string(smem_for(std::max(epb, unit))) + " B needed)"));
   e->dense = meshed;
   e->G = G; e->threads = epb * G; e->epb = epb; e->smem = static_cast<int>(smem_for(epb));
   {   // helper warps (next profile rows + noise, concurrent with the Newton iteration): one per 256 Box-Muller pairs of a
@@ -829,7 +854,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   P.slack_bus = slack;
   P.nb = cfg->batch; P.env_stride2 = stride2; P.pvq_off2 = pvq_off2; P.scratch_off2 = scratch_off2; P.hot_layout = hl;
   P.helper_off = hl.bytes + e->epb * stride2 * 16;
-  P.stage_in_records = stage_fits_records(npq, nl) ? 1 : 0;
+  P.stage_in_records = stage_rec ? 1 : 0;
   P.obs_skip_off = -1;
   e->obs_zero_off = 2 * (npq * kNodeArrays2 + A_UP);
   {   // bus shunts by node (res_bus p/q carry the shunt power, pandapower _get_shunt_results)
@@ -852,7 +877,6 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     const double* d_ysl = nullptr;
     TRY(dev_upload(e, ysl_cold, &d_ysl));
     P.ysl = reinterpret_cast<const double2*>(d_ysl);
-    if (line_nodes.empty()) { line_nodes.assign(2, 0); line_c.assign(4, 0.0); }
     TRY(dev_upload(e, obs_off, &P.obs_off)); TRY(dev_upload(e, line_nodes, &P.line_nodes)); TRY(dev_upload(e, line_c, &P.line_c));
   }
   {

@@ -379,6 +379,10 @@ class VoltageControl:
         self.steps = 1
         self.sum_rewards = 0
         self.obs_history = {i: [] for i in range(self.n_agents)}
+        # reset wrote obs / state of the new episode into the env's device buffers: one copy each, then get_obs() /
+        # get_state() are served from the host until the next transition (no kernel, no sync per getter call)
+        self._obs_host = self._env.obs[0].cpu().numpy()
+        self._state_host = self._env.state[0].cpu().numpy()
         return self.get_obs(), self.get_state()
 
     def reset(self, reset_time=True):
@@ -409,9 +413,10 @@ class VoltageControl:
     # ---- step ----------------------------------------------------------------------------------
     def step(self, actions, add_noise=True):
         a = np.asarray(actions, dtype=np.float64).reshape(1, self.n_agents)
-        r, t, info, _ = self._env.step_host(a, add_noise=add_noise)
+        r, t, info, obs = self._env.step_host(a, add_noise=add_noise)      # one launch; results land in pinned host memory
         reward, terminated = float(r[0]), bool(t[0])
         info = {k: float(v) for k, v in zip(INFO_KEYS, info[0])}
+        self._obs_host, self._state_host = obs[0].copy(), None
         self.steps += 1
         self.sum_rewards += reward
         if terminated:
@@ -420,10 +425,12 @@ class VoltageControl:
 
     # ---- observations --------------------------------------------------------------------------
     def get_state(self):
-        return self._env.get_state()[0].cpu().numpy()
+        if self._state_host is None:
+            self._state_host = self._env.get_state()[0].cpu().numpy()
+        return self._state_host.copy()
 
     def get_obs(self):
-        obs = self._env.get_obs()[0].cpu().numpy()
+        obs = self._obs_host
         agents_obs = [obs[i].copy() for i in range(self.n_agents)]
         if self.history > 1:                                          # reference :303-315
             agents_obs_ = []

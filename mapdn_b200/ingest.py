@@ -317,10 +317,54 @@ def load_scenario(data_path: str, pv_scale: float = 1.0, demand_scale: float = 1
     return net, prof
 
 
-if __name__ == "__main__":          # python -m mapdn_b200.ingest <data_path> [out.npz]
+def verify_report(data_path: str, device: int = 0) -> dict:
+    """Self-check for whoever has the real scenario files (reference README.md:98-107): ingest ``data_path``, solve the
+    net on the GPU at the first profile row with q = 0 (no control) and return the numbers a pandapower user can compare
+    with ``pp.runpp(pp.from_pickle("model.p"))`` on the same row: sizes, zone sizes, V_min / V_max and their buses, total
+    line loss, ext-grid infeed, Newton iterations, KCL residual of the solution against the ingested Ybus."""
+    import torch
+    from .env import BatchedVoltageControl
+    net, prof = load_scenario(data_path)
+    env = BatchedVoltageControl(net, None, None, batch=1, device=device)
+    row = 0
+    pl, ql, pv = prof.load_p[row][None], prof.load_q[row][None], prof.pv[row][None]
+    out = env.solve(pl, ql, pv, np.zeros_like(pv))
+    torch.cuda.synchronize()
+    vm = out["vm"].cpu().numpy()[0]
+    va = np.deg2rad(out["va_deg"].cpu().numpy()[0])
+    V = vm * np.exp(1j * va)
+    Y = env.ybus_dense()
+    pd = np.zeros(net.n_bus); qd = np.zeros(net.n_bus)
+    np.add.at(pd, net.load_bus, pl[0] * net.load_scaling); np.add.at(qd, net.load_bus, ql[0] * net.load_scaling)
+    np.add.at(pd, net.sgen_bus, -pv[0] * net.sgen_scaling)
+    mis = V * np.conj(Y @ V) + (pd + 1j * qd) / net.base_mva
+    mis[net.slack_bus] = 0.0
+    zones = {str(net.zone_names[z]) if z < len(net.zone_names) else int(z): int((net.bus_zone == z).sum())
+             for z in sorted(set(net.bus_zone.tolist()))}
+    rep = dict(data_path=os.path.abspath(data_path), n_bus=int(net.n_bus), n_branch=int(net.n_branch),
+               n_line=int(net.br_is_line.sum()), n_trafo=int(net.n_branch - net.br_is_line.sum()), n_load=int(net.n_load),
+               n_sgen=int(net.n_sgen), base_mva=float(net.base_mva), slack_bus=int(net.slack_bus), slack_vm=float(net.slack_vm),
+               zone_sizes=zones, obs_dim=int(env.obs_size), state_dim=int(env.state_size),
+               profile_rows=int(prof.n_rows), steps_per_hour=int(prof.steps_per_hour), n_days=int(prof.n_days),
+               s_max_mva=[float(x) for x in prof.s_max], row=row, converged=bool(out["converged"][0]),
+               newton_iterations=int(out["iterations"][0]), v_min_pu=float(vm.min()), v_min_bus=int(vm.argmin()),
+               v_max_pu=float(vm.max()), v_max_bus=int(vm.argmax()), total_line_loss_mw=float(out["pl"].sum()),
+               ext_grid_p_mw=float(-out["p_bus"][0, net.slack_bus]), ext_grid_q_mvar=float(-out["q_bus"][0, net.slack_bus]),
+               kcl_residual_pu=float(np.abs(mis).max()), solver="meshed (dense LU)" if env.dims["n_levels"] == 1 and net.n_bus > 2
+               else "radial (tree elimination)")
+    env.close()
+    return rep
+
+
+if __name__ == "__main__":          # python -m mapdn_b200.ingest <data_path> [out.npz] | --verify <data_path>
+    import json
     import sys
+    if len(sys.argv) >= 3 and sys.argv[1] == "--verify":
+        print(json.dumps(verify_report(sys.argv[2]), indent=1))
+        sys.exit(0)
     if len(sys.argv) < 2:
-        sys.exit("usage: python -m mapdn_b200.ingest <scenario directory> [out.npz]")
+        sys.exit("usage: python -m mapdn_b200.ingest <scenario directory> [out.npz]\n"
+                 "       python -m mapdn_b200.ingest --verify <scenario directory>   (needs a GPU)")
     _net, _prof = load_scenario(sys.argv[1])
     _out = save_scenario_npz(sys.argv[2] if len(sys.argv) > 2 else sys.argv[1], _net, _prof)
     print(f"{_out}: {_net.n_bus} buses, {_net.n_load} loads, {_net.n_sgen} sgens, {_prof.n_rows} rows")

@@ -212,3 +212,19 @@ def test_marl_runner_on_device():
     assert np.isfinite(ev["mean_test_reward"]) and ev["mean_test_destroy"] == 0.0
     print(f"learner-inclusive throughput: {runner.steps / dt / 1e3:.1f} k env-steps/s (B={B}, tiny actor-critic, "
           f"one critic update per lock-step)")
+
+
+def test_ingest_verify_report(tmp_path):
+    """`python -m mapdn_b200.ingest --verify <dir>`: the numbers somebody with the real files compares with pandapower."""
+    from mapdn_b200 import ingest
+    from oracle.pandapower_nr import PandapowerEquivalent
+    net, prof = cases.make_case("case33"), cases.make_profiles("case33", n_days=3)
+    ingest.save_scenario_npz(str(tmp_path), net, prof)
+    rep = ingest.verify_report(str(tmp_path))
+    r = PandapowerEquivalent(net).runpp(prof.load_p[0], prof.load_q[0], prof.pv[0], np.zeros(net.n_sgen))
+    assert rep["n_bus"] == 33 and rep["n_load"] == 32 and rep["n_sgen"] == 6 and rep["obs_dim"] == 50
+    assert rep["zone_sizes"] == {"main": 6, "zone1": 12, "zone2": 4, "zone3": 3, "zone4": 8}
+    assert rep["converged"] and rep["newton_iterations"] == r.iterations
+    assert abs(rep["v_min_pu"] - r.vm_pu.min()) < 1e-9 and rep["v_min_bus"] == int(r.vm_pu.argmin())
+    assert abs(rep["total_line_loss_mw"] - r.pl_mw.sum()) < 1e-9 and abs(rep["ext_grid_p_mw"] - r.p_ext_mw) < 1e-9
+    assert rep["kcl_residual_pu"] < 1e-8 and rep["solver"].startswith("radial")
