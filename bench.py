@@ -424,14 +424,16 @@ def measure(sc, barrier, global_batch, K, W, Ke, tm, local, rank, flush, lanes=0
     return out
 
 
-def roofline_of(m, peak, peak_src, traffic=None):
+def roofline_of(m, peak, peak_src, traffic=None, ncu=None):
     ms = m["ms_per_step"]
     achieved = m["_alg_bytes_per_launch"] / (ms * 1e-3) / 1e9
     return dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
                 peak_source=f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback 6.65 TB/s",
                 kernel=f"env_kernel<{m['lanes_per_env']},STEP>", algorithmic_bytes_per_launch=m["_alg_bytes_per_launch"],
-                binding_bound="fp64-issue / dependent-latency / shared-memory pipe (DESIGN.md §4): the fused kernel "
-                              "moves ~3.6 kB of compulsory HBM traffic per env-step, far below the HBM roof")
+                ncu=ncu,
+                binding_bound="dependent-instruction latency of the slowest env of the launch (5 Newton iterations), fp64 issue "
+                              "inside a sweep step, shared-memory pipe (DESIGN.md §4); compulsory HBM traffic is a few kB per "
+                              "env-step, far below the HBM roof")
 
 
 def parity_check(sc, barrier, B, local, n_check=64, n_steps=3):
@@ -539,7 +541,7 @@ def run_ours(args):
     except Exception:
         pass
     net = cases.make_case(sc)
-    roofline = roofline_of(m, peak, peak_src, traffic.get(f"{sc}_B{B}"))
+    roofline = roofline_of(m, peak, peak_src, traffic.get(f"{sc}_B{B}"), (traffic.get("ncu") or {}).get(f"{sc}_B{B}"))
     for r in subs:
         r["roofline"] = roofline_of(r, peak, peak_src, traffic.get(f"{r['scenario']}_B{r['envs_per_gpu']}"))
         r["config"] = dict(workload=workload_string(r["scenario"], r["envs_per_gpu"], r["barrier"]))
