@@ -578,6 +578,138 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
                          (static_cast<uint64_t>(kBschedRegParent | kBschedIdle) << 32));
   const int n_esteps = static_cast<int>(esched.size()) / G, n_bsteps = static_cast<int>(bsched.size()) / G;
 
+  // ---- 2b. bank-conflict-aware relabelling of the node records ----
+  // A node record is 144 B = 9 x 16 B, so the 16-byte bank group of field f of node i is (i + f) mod 8: the eight lanes of a
+  // quarter-warp (one 128-bit access wavefront) are conflict free iff their node ids differ mod 8. The passes own nodes
+  // by id (conflict free by construction) but reach parents / children by pointer, and the sweeps touch whatever the
+  // schedules say; ncu counted 25 % of the shared-load wavefronts as conflicts with the breadth-first ids. The ids are
+  // free to choose, so pick a permutation that minimises the weighted number of extra wavefronts over every access group
+  // of the kernel (simulated annealing on pairwise swaps, deterministic; identity when it does not apply).
+  std::vector<int> kid0(npq, npq), kid1(npq, npq);
+  for (int i = 0; i < npq; ++i) { if (nchild[i] > 0) kid0[i] = cfirst[i]; if (nchild[i] > 1) kid1[i] = cfirst[i] + 1; }
+  double relabel_cost0 = 0.0, relabel_cost1 = 0.0;
+  if (!meshed && max_children <= 2 && G >= 8 && npq >= 8 && !getenv("MAPDN_NO_RELABEL")) {
+    struct Grp { std::vector<int> nodes; double w; };
+    std::vector<Grp> groups;                                  // groups whose members do not depend on the labelling
+    const double w_iter = 4.5;                                // Newton iterations per step (sweeps and passes run that often)
+    auto add_quarters = [&](const std::vector<int>& per_lane, double w) {      // per_lane: node per lane of the group (-1: no access)
+      for (int q = 0; q < G / 8; ++q) {
+        Grp g; g.w = w;
+        for (int l = 8 * q; l < 8 * q + 8; ++l) if (per_lane[l] >= 0) g.nodes.push_back(per_lane[l]);
+        std::sort(g.nodes.begin(), g.nodes.end());
+        g.nodes.erase(std::unique(g.nodes.begin(), g.nodes.end()), g.nodes.end());      // same address = broadcast
+        if (g.nodes.size() > 1) groups.push_back(std::move(g));
+      }
+    };
+    std::vector<int> own(G), c0v(G), c1v(G);
+    for (size_t st = 0; st < esched.size() / G; ++st) {
+      for (int l = 0; l < G; ++l) {
+        const uint64_t ed = esched[st * G + l];
+        const unsigned fl = static_cast<unsigned>(ed >> 48);
+        own[l] = static_cast<int>(ed & 0xFFFFu);
+        c0v[l] = (fl & kEschedLoad0) ? static_cast<int>((ed >> 16) & 0xFFFFu) : -1;
+        c1v[l] = (fl & kEschedLoad1) ? static_cast<int>((ed >> 32) & 0xFFFFu) : -1;
+      }
+      add_quarters(own, 2.0 * w_iter);                        // own blocks: loaded (prefetch) and stored
+      add_quarters(c0v, w_iter); add_quarters(c1v, w_iter);
+    }
+    for (size_t st = 0; st < bsched.size() / G; ++st) {
+      for (int l = 0; l < G; ++l) {
+        const uint64_t bd = bsched[st * G + l];
+        const unsigned bfl = static_cast<unsigned>(bd >> 32);
+        own[l] = static_cast<int>(bd & 0xFFFFu);
+        c0v[l] = (bfl & (kBschedRegParent | kBschedIdle)) ? -1 : static_cast<int>((bd >> 16) & 0xFFFFu);
+      }
+      add_quarters(own, 2.0 * w_iter); add_quarters(c0v, w_iter);
+    }
+    for (int b0 = 0; b0 < n; b0 += G) {                       // epilogue: per-bus loop, buses b0 + lane
+      for (int l = 0; l < G; ++l) own[l] = (b0 + l < n) ? node_of_bus[b0 + l] : -1;
+      add_quarters(own, 1.0);
+    }
+    {
+      std::vector<int> lf, lt;
+      for (int k = 0; k < nbr; ++k) if (br_line[k]) { lf.push_back(node_of_bus[e->br_from[k]]); lt.push_back(node_of_bus[e->br_to[k]]); }
+      for (size_t k0 = 0; k0 < lf.size(); k0 += G) {
+        for (int l = 0; l < G; ++l) { own[l] = (k0 + l < lf.size()) ? lf[k0 + l] : -1; c0v[l] = (k0 + l < lt.size()) ? lt[k0 + l] : -1; }
+        add_quarters(own, 1.0); add_quarters(c0v, 1.0);
+      }
+    }
+    // lab[base id] = label; sentinel / trash keep their ids
+    std::vector<int> lab(npq + 2), inv(npq + 2);
+    for (int i = 0; i < npq + 2; ++i) lab[i] = inv[i] = i;
+    auto extra = [&](const int* ids, int cnt) {               // extra wavefronts of one access: max multiplicity - 1
+      int c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      int mx = 0;
+      for (int k = 0; k < cnt; ++k) mx = std::max(mx, ++c[ids[k] & 7]);
+      return std::max(0, mx - 1);
+    };
+    auto cost = [&]() {
+      double tot = 0.0;
+      int ids[8];
+      for (const Grp& g : groups) {
+        int cnt = 0;
+        for (int v : g.nodes) ids[cnt++] = lab[v];
+        tot += g.w * extra(ids, cnt);
+      }
+      // passes: label L is handled by lane L % G in round L / G; neighbours reached by pointer
+      for (int L0 = 0; L0 < npq; L0 += 8) {
+        int pa[8], k0[8], k1[8], np = 0, n0 = 0, n1 = 0;
+        auto push_unique = [](int* a, int& cnt, int v) { for (int k = 0; k < cnt; ++k) if (a[k] == v) return; a[cnt++] = v; };
+        for (int L = L0; L < std::min(npq, L0 + 8); ++L) {
+          const int i = inv[L];
+          push_unique(pa, np, parent[i] >= 0 ? lab[parent[i]] : npq);
+          push_unique(k0, n0, lab[kid0[i]]); push_unique(k1, n1, lab[kid1[i]]);
+        }
+        tot += w_iter * (extra(pa, np) + extra(k0, n0) + extra(k1, n1));
+      }
+      return tot;
+    };
+    relabel_cost0 = cost();
+    double cur = relabel_cost0, best = cur;
+    std::vector<int> best_lab = lab;
+    uint64_t rng = 0x9E3779B97F4A7C15ull;
+    auto rnd = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
+    const int iters = std::min(400 * npq, 30000);
+    double T = std::max(1.0, 0.02 * cur);
+    const double cool = std::pow(1e-3, 1.0 / std::max(1, iters));
+    for (int it = 0; it < iters && best > 0.0; ++it, T *= cool) {
+      const int a = static_cast<int>(rnd() % npq), b = static_cast<int>(rnd() % npq);
+      if (a == b || ((lab[a] ^ lab[b]) & 7) == 0) continue;  // same residue: no effect on any group
+      std::swap(lab[a], lab[b]); inv[lab[a]] = a; inv[lab[b]] = b;
+      const double c2 = cost();
+      const double u = static_cast<double>(rnd() >> 11) * (1.0 / 9007199254740992.0);
+      if (c2 <= cur || u < std::exp((cur - c2) / T)) {
+        cur = c2;
+        if (cur < best) { best = cur; best_lab = lab; }
+      } else {
+        std::swap(lab[a], lab[b]); inv[lab[a]] = a; inv[lab[b]] = b;
+      }
+    }
+    lab = best_lab;
+    relabel_cost1 = best;
+    if (best < relabel_cost0) {
+      // apply: new id of base node i is lab[i]
+      std::vector<int> order2(npq), parent2(npq), nchild2(npq), k0b(npq), k1b(npq);
+      for (int i = 0; i < npq; ++i) {
+        const int L = lab[i];
+        order2[L] = order[i];
+        parent2[L] = parent[i] >= 0 ? lab[parent[i]] : -1;
+        nchild2[L] = nchild[i];
+        k0b[L] = lab[kid0[i]]; k1b[L] = lab[kid1[i]];
+      }
+      order = order2; parent = parent2; nchild = nchild2; kid0 = k0b; kid1 = k1b;
+      for (int i = 0; i < npq; ++i) node_of_bus[order[i]] = i;
+      auto map16 = [&](uint64_t v) { return static_cast<uint64_t>(lab[static_cast<int>(v & 0xFFFFu)]); };
+      for (uint64_t& ed : esched)
+        ed = (ed & 0xFFFF000000000000ull) | map16(ed) | (map16(ed >> 16) << 16) | (map16(ed >> 32) << 32);
+      for (uint64_t& bd : bsched)
+        bd = (bd & 0xFFFFFFFF00000000ull) | map16(bd) | (map16(bd >> 16) << 16);
+    }
+    if (getenv("MAPDN_DEBUG_SCHED"))
+      fprintf(stderr, "[relabel] weighted extra shared-memory wavefronts per env-step: %.1f -> %.1f (%d swaps tried)\n",
+              relabel_cost0, relabel_cost1, iters);
+  }
+
   // ---- 3. element -> node maps (needed by the hot blob) ----
   const int na = npq + 2;      // + sentinel + trash records
   std::vector<uint16_t> lptr(npq + 2, 0), lidx(std::max(1, nl)), sptr(npq + 2, 0), sidx(ng), xptr(npq + 2, 0), xidx;
@@ -733,7 +865,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
       }
       // parent | child0 | child1 | number of further children (contiguous after child1); npq = zero slot
       const uint64_t pa = parent[i] >= 0 ? static_cast<uint64_t>(parent[i]) : npq;   // roots: sentinel, Y = 0
-      const uint64_t c0 = nchild[i] > 0 ? cfirst[i] : npq, c1 = nchild[i] > 1 ? cfirst[i] + 1 : npq;
+      const uint64_t c0 = static_cast<uint64_t>(kid0[i]), c1 = static_cast<uint64_t>(kid1[i]);   // npq = none
       const uint64_t nx = nchild[i] > 2 ? nchild[i] - 2 : 0;
       const uint64_t sl_adj = pairs.count({std::min(b, slack), std::max(b, slack)}) ? 1 : 0;
       ndesc[i] = pa | (c0 << 16) | (c1 << 32) | (nx << 48) | (sl_adj << 63);

@@ -30,7 +30,10 @@ def make_ybus(net):
     Returns (Ybus csr [nb,nb], Yf csr [nbr,nb], Yt csr [nbr,nb])."""
     nb, nbr = net.n_bus, net.br_from.shape[0]
     stat = net.br_status.astype(np.float64)
-    Ys = stat / (net.br_r + 1j * net.br_x)
+    # pandapower drops out-of-service branches in _ppc2ppci before makeYbus; here they stay as all-zero rows (so that Yf / Yt
+    # keep the branch numbering) - also when r = x = 0
+    z = net.br_r + 1j * net.br_x
+    Ys = np.where(stat > 0, stat / np.where(stat > 0, z, 1.0), 0.0)
     Bc = stat * (net.br_b - 1j * net.br_g)           # complex "b": b - j g
     tap = np.where(net.br_tap == 0.0, 1.0, net.br_tap).astype(np.complex128)
     tap = tap * np.exp(1j * np.pi / 180.0 * net.br_shift)

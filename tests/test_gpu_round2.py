@@ -228,3 +228,21 @@ def test_ingest_verify_report(tmp_path):
     assert abs(rep["v_min_pu"] - r.vm_pu.min()) < 1e-9 and rep["v_min_bus"] == int(r.vm_pu.argmin())
     assert abs(rep["total_line_loss_mw"] - r.pl_mw.sum()) < 1e-9 and abs(rep["ext_grid_p_mw"] - r.p_ext_mw) < 1e-9
     assert rep["kcl_residual_pu"] < 1e-8 and rep["solver"].startswith("radial")
+
+
+def test_out_of_service_zero_impedance_branch_contributes_nothing():
+    """makeYbus multiplies by the status: a disconnected branch with r = x = 0 must not poison the diagonal with NaN."""
+    net = NetDesc(base_mva=1.0, n_bus=3, slack_bus=0, slack_vm=1.0, br_from=np.array([0, 1, 0]), br_to=np.array([1, 2, 2]),
+                  br_r=np.array([0.01, 0.02, 0.0]), br_x=np.array([0.02, 0.03, 0.0]),
+                  br_status=np.array([1, 1, 0], np.uint8), load_bus=np.array([1, 2]), sgen_bus=np.array([2]),
+                  sgen_zone=np.array([1]), bus_zone=np.array([0, 1, 1]), name="open3")
+    from oracle.pandapower_nr import PandapowerEquivalent
+    env = _make(net, None, None, batch=1)
+    Y = env.ybus_dense()
+    assert np.isfinite(Y.real).all() and np.isfinite(Y.imag).all()
+    pl, ql = np.array([[0.3, 0.2]]), np.array([[0.1, 0.05]])
+    out = env.solve(pl, ql, np.array([[0.1]]), np.array([[0.02]]))
+    torch.cuda.synchronize()
+    with np.errstate(all="ignore"):
+        r = PandapowerEquivalent(net).runpp(pl[0], ql[0], np.array([0.1]), np.array([0.02]))
+    assert int(out["converged"][0]) == 1 and np.abs(out["vm"][0].cpu().numpy() - r.vm_pu).max() < 1e-10
