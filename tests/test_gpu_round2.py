@@ -246,3 +246,22 @@ def test_out_of_service_zero_impedance_branch_contributes_nothing():
     with np.errstate(all="ignore"):
         r = PandapowerEquivalent(net).runpp(pl[0], ql[0], np.array([0.1]), np.array([0.02]))
     assert int(out["converged"][0]) == 1 and np.abs(out["vm"][0].cpu().numpy() - r.vm_pu).max() < 1e-10
+
+
+def test_node_relabelling_changes_addresses_not_results(monkeypatch):
+    """The bank-conflict-aware node ids (mapdn_create, section 2b) only move records inside shared memory: rewards, info,
+    observations and voltages are bit-identical with and without them."""
+    net, prof = cases.make_case("case33"), cases.make_profiles("case33", n_days=4)
+    args = dict(seed=6, voltage_barrier_type="bowl")
+    monkeypatch.setenv("MAPDN_NO_RELABEL", "1")
+    e0 = _make(net, prof, args, batch=40)
+    monkeypatch.delenv("MAPDN_NO_RELABEL")
+    e1 = _make(net, prof, args, batch=40)
+    o0, s0 = e0.reset(); o1, s1 = e1.reset()
+    assert torch.equal(o0, o1) and torch.equal(s0, s1)
+    rng = np.random.default_rng(0)
+    for _ in range(3):
+        a = torch.tensor(rng.uniform(-0.8, 0.8, (40, 6)), device=e0.device)
+        r0, t0, i0 = e0.step(a); r1, t1, i1 = e1.step(a)
+        assert torch.equal(r0, r1) and torch.equal(t0, t1) and torch.equal(i0, i1) and torch.equal(e0.obs, e1.obs)
+        assert torch.equal(e0.get_field("vm"), e1.get_field("vm")) and torch.equal(e0.get_state(), e1.get_state())
