@@ -8,8 +8,10 @@
 // admittances, the elimination schedule, the element->bus maps and the observation program
 // (identical for all envs) are staged once per CTA with a TMA bulk copy. The Newton loop never
 // touches HBM and is written branch-light: every "missing child" points at an all-zero slot.
-// In MODE_STEP one extra (helper) warp per CTA draws the next profile rows + noise of the CTA's
+// In MODE_STEP one to four extra (helper) warps per CTA draw the next profile rows + noise of the CTA's
 // envs concurrently with the Newton iteration (warp specialisation, two named barriers).
+// MODE_DROOP runs the paper's droop-control baseline (a relaxed loop of power flows) inside the same kernel; the host
+// path can hand the kernel pinned host memory for actions / results (mapdn_step_host_pinned: no staging copies).
 //
 // The linear solve works on the forest of PQ buses (the slack bus is not an unknown), each tree
 // re-rooted at its centre so that the leaf->root elimination has half the depth of the feeder.
@@ -17,7 +19,7 @@
 // Replaces, per env: reference voltage_control_env.py step :178-211, _take_action :548-566,
 // _clip_reactive_power :568-572, pp.runpp (pandapower 2.7.0 newtonpf),
 // _calc_reward :574-623, voltage_barrier/*.py, _set_demand_and_pv :491-513, get_obs :232-316,
-// reset/manual_reset :96-176.
+// reset/manual_reset :96-176; traditional_control/pf_droop_matpower_all.m:121-152,196-231 (MODE_DROOP).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -5,8 +5,10 @@
 namespace mapdn {
 
 // Per-env shared memory: (npq + 2) node records of 9 double2 (144 B, array-of-structs: one address
-// computation per node, 128-bit accesses; consecutive nodes are bank-conflict free), then the sgen
-// block (pv | q), then a scratch region of ng + 2 n_load doubles (DESIGN.md "shared-memory layout").
+// computation per node, 128-bit accesses; the bank group of field f of node i is (i + f) mod 8, so node ids that differ
+// mod 8 never conflict - mapdn_create picks the ids accordingly), then the sgen block (pv | q), then a scratch region:
+// [n_sgen] next pv row / droop voltages, the partials of the multi-warp reductions, and the staged loads unless they are
+// staged inside the records.
 // Record npq is a sentinel: the slack bus in VV / EF / SP, all-zero in UP / DN / T / R (the "no child" /
 // "no parent" slot of the branch-free gathers). Record npq + 1 is a trash record: idle lanes of a
 // schedule step work on it so that the level sweeps have no divergent branches.
