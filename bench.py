@@ -243,9 +243,10 @@ class ClockSampler:
                                      int(reasons(h))))
             except Exception:
                 break
-            time.sleep(0.002)
+            time.sleep(0.0005)
 
     def start(self):
+        self.t_start = time.perf_counter()
         try:
             self.nvml = self._nvml_open()
             self.th = threading.Thread(target=self._poll, daemon=True)
@@ -266,17 +267,24 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.rows.append((time.perf_counter(), ln.strip()))
 
-    def stop(self, t0, t1):
+    def stop(self, t0, t1, t_load0=None):
+        """Samples inside the timed region [t0, t1]; when the region is too short for three samples (20 steps last ~2.5 ms)
+        the window is widened to the loaded period that contains it (warm-up steps + timed steps, from t_load0)."""
         if self.nvml is not None:
             self._stop.set()
             self.th.join(timeout=1.0)
-            rows = [r for r in self.samples if t0 <= r[0] <= t1] or self.samples[-3:]
+            timed = [r for r in self.samples if t0 <= r[0] <= t1]
+            rows, window = timed, "timed region"
+            if len(rows) < 3 and t_load0 is not None:
+                rows, window = [r for r in self.samples if t_load0 <= r[0] <= t1], "warm-up + timed region (GPU under the same load)"
+            rows = rows or self.samples[-3:]
             if rows:
                 bits = 0
                 for r in rows:
                     bits |= r[2]
                 return dict(sm_mhz=float(np.median([r[1] for r in rows])), sm_max_mhz=self.nvml[3],
-                            reasons=sorted(nm for nm, b in self.REASON_BITS if bits & b), samples=len(rows), source="nvml")
+                            reasons=sorted(nm for nm, b in self.REASON_BITS if bits & b), samples=len(rows),
+                            samples_in_timed_region=len(timed), window=window, source="nvml")
             return None
         if self.proc is None:
             return None
@@ -325,7 +333,8 @@ class Timer:
         return float(t.item())
 
 
-def measure(sc, barrier, global_batch, K, W, Ke, tm, local, rank, flush, lanes=0, clocks=None, obs_dtypes=("f64",)):
+def measure(sc, barrier, global_batch, K, W, Ke, tm, local, rank, flush, lanes=0, clocks=None, obs_dtypes=("f64",),
+            min_warm=0):
     """Device-timed and end-to-end throughput of one configuration, sharded over the ranks of this job."""
     import torch
     from mapdn_b200 import cases
@@ -351,15 +360,18 @@ def measure(sc, barrier, global_batch, K, W, Ke, tm, local, rank, flush, lanes=0
         state["t"] += 1
 
     env.reset()
+    if clocks is not None:
+        clocks.start()
+        time.sleep(0.05)
+    tm.sync_all()
+    t_load0 = time.perf_counter()
+    W = max(W, min_warm)              # every rank alike; the clock record needs some loaded time before the timed steps
     for i in range(W):
         one_step(i)
         if flush is not None:
             flush.zero_()
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    if clocks is not None:
-        clocks.start()
-        time.sleep(0.15)
     tm.sync_all()
     launches0 = env.launch_count
     w0 = time.perf_counter()
@@ -373,7 +385,7 @@ def measure(sc, barrier, global_batch, K, W, Ke, tm, local, rank, flush, lanes=0
     tm.sync_all()
     w1 = time.perf_counter()
     launches = env.launch_count - launches0
-    clk = clocks.stop(w0, w1) if clocks is not None else None
+    clk = clocks.stop(w0, w1, t_load0) if clocks is not None else None
     dev_ms = tm.max_over_ranks(sum(a.elapsed_time(b) for a, b in zip(ev0, ev1)))
     assert returns.shape[0] == global_batch and bool(torch.isfinite(returns).all())
     # side metrics of the last timed step: Newton iterations per solve, diverged fraction
@@ -389,7 +401,7 @@ def measure(sc, barrier, global_batch, K, W, Ke, tm, local, rank, flush, lanes=0
                lanes_per_env=env.dims["lanes_per_env"], envs_per_block=env.dims["envs_per_block"],
                smem_bytes_per_block=env.dims["smem_bytes"], n_bus=net.n_bus, n_agents=net.n_sgen, obs_dim=env.obs_size,
                newton_iters_mean=float(side[0].item()), nonconverged_frac=float(side[1].item()),
-               gpu_launches=int(launches), wall_ms_per_step=(w1 - w0) / K * 1e3)
+               gpu_launches=int(launches), wall_ms_per_step=(w1 - w0) / K * 1e3, warmup_steps_done=W)
     alg = env.dims["algorithmic_bytes_per_env_step"] * B            # per launch (this GPU's shard)
     out["_alg_bytes_per_launch"] = alg
     out["_clocks"] = clk
@@ -503,7 +515,7 @@ def run_ours(args):
         parity = parity_check(sc, barrier, B, local)
     clocks = ClockSampler(local) if rank == 0 else None
     m = measure(sc, barrier, B * world, K, W, Ke, tm, local, rank, flush, lanes=args.lanes, clocks=clocks,
-                obs_dtypes=("f64", "f32", "staged"))
+                obs_dtypes=("f64", "f32", "staged"), min_warm=50)
 
     # ---- the other BASELINE.json configurations of this GPU count ----
     subs = []
@@ -566,6 +578,7 @@ def run_ours(args):
                             n_bus=net.n_bus, n_agents=net.n_sgen, obs_dim=m["obs_dim"], global_batch=B * world,
                             lanes_per_env=m["lanes_per_env"], envs_per_block=m["envs_per_block"],
                             parallelism=f"envs sharded over {world} GPU(s)", numa=numa,
+                            warmup_steps_done=m["warmup_steps_done"],
                             l2="flushed between steps (256 MiB memset, outside the event pairs)" if flush is not None
                             else "not flushed", timing="sum of per-step CUDA-event pairs, max over ranks"),
                 clocks=m["_clocks"], gpu_launches=m["gpu_launches"],

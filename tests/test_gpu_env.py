@@ -71,7 +71,7 @@ def test_trajectory_matches_oracle(name, barrier, lanes, add_noise):
     args = dict(voltage_barrier_type=barrier, action_scale=cases.SCENARIOS[name]["action_scale"], seed=5)
     B = 21
     env = _make(net, prof, args, batch=B, lanes_per_env=lanes, env_id_offset=1000)
-    ids = [0, 7, B - 1]
+    ids = [0, 7, B - 1] if name == "case322" else [0, 3, 7, 12, 16, B - 1]      # the case322 oracle is the slow part
     oracles = [VoltageControlOracle(net, prof, env.args, env_id=1000 + i) for i in ids]
     if add_noise:
         obs, state = env.reset()
