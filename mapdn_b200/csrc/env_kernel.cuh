@@ -369,13 +369,16 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
       };
       // two instantiations (nets with / without a bus of degree > 3): tested inside the loop, the flag was re-fetched from the
       // constant bank on every step (ncu: 10 % of the loop's stall samples on LDCU / compare / branch)
-      auto sweep = [&](auto with_extra) {
-      constexpr bool kExtra = decltype(with_extra)::value;
-      uint64_t ed = h.esched[gl];
-      uint64_t ed_next = h.esched[max(0, min(1, p.n_esteps - 1)) * G + gl];
-      Own own = load_own(ed);
       double2 s01 = make_double2(0.0, 0.0), s23 = s01, tt = s01;     // Schur update produced by this lane's last step
-      for (int st = 0; st < p.n_esteps; ++st) {
+      // steps [st0, st1); warp_only: a narrow phase of a multi-warp group - only warp 0 is here, it synchronises with itself
+      auto sweep = [&](auto with_extra, auto warp_only, int st0, int st1) {
+      constexpr bool kExtra = decltype(with_extra)::value;
+      constexpr bool kWarpOnly = decltype(warp_only)::value;
+      if (st0 >= st1) return;
+      uint64_t ed = h.esched[st0 * G + gl];
+      uint64_t ed_next = h.esched[min(st0 + 1, p.n_esteps - 1) * G + gl];
+      Own own = load_own(ed);
+      for (int st = st0; st < st1; ++st) {
         PROF_STEP_BEGIN
         const uint64_t ed_next2 = h.esched[min(st + 2, p.n_esteps - 1) * G + gl];   // independent of the data
         const int i = static_cast<int>(ed & 0xFFFFu);
@@ -384,7 +387,7 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
         double2* nd = s.node(i);
         double2 d01 = own.d01, d23 = own.d23, r = own.r;
         const double2 u = own.u, d = own.d;   // J[i,p] = [[a,b],[-b,a]](u), J[p,i] likewise (d); zero at roots
-        grp_sync<G>(gidx);                                    // the previous step's Schur updates are visible
+        if (kWarpOnly) __syncwarp(); else grp_sync<G>(gidx);  // the previous step's Schur updates are visible
         // child 0: this lane's registers (chain) or shared memory (a leaf reads the all-zero sentinel record)
         double2 p01 = s01, p23 = s23, pt = tt;
         if (fl & kEschedLeaf) { p01 = make_double2(0.0, 0.0); p23 = p01; pt = p01; }     // a lane starting a new chain
@@ -430,7 +433,20 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
         PROF_STEP_END
       }
       };
-      if (extra_children) sweep(std::true_type{}); else sweep(std::false_type{});
+      // G > 32: the levels near the roots fit one warp (host schedule: lanes 0..31 from step n_wide_e on) - warp 0 runs them
+      // with __syncwarp while the other warps of the group wait at the barrier behind the sweep (case322: 14 of 19 steps)
+      auto run_sweep = [&](auto with_extra) {
+        if constexpr (G <= 32) {
+          sweep(with_extra, std::false_type{}, 0, p.n_esteps);
+        } else {
+          sweep(with_extra, std::false_type{}, 0, p.n_wide_e);
+          if (p.n_wide_e < p.n_esteps) {
+            if (p.n_wide_e > 0) grp_sync<G>(gidx);           // the last wide step's updates are visible to warp 0
+            if ((gl >> 5) == 0) sweep(with_extra, std::true_type{}, p.n_wide_e, p.n_esteps);
+          }
+        }
+      };
+      if (extra_children) run_sweep(std::true_type{}); else run_sweep(std::false_type{});
       PROF_COUNT(15)
       grp_sync<G>(gidx);                                 // the last step's results are visible to the back sweep
     }
@@ -444,15 +460,18 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
         OwnB o; o.m01 = nd[A_D01]; o.m23 = nd[A_D23]; o.x = nd[A_R];
         return o;
       };
-      uint64_t bd = h.bsched[gl];
-      uint64_t bd_next = h.bsched[max(0, min(1, p.n_bsteps - 1)) * G + gl];
-      OwnB own = load_own(bd);
       double2 xl = make_double2(0.0, 0.0);               // dx of the node this lane solved in the previous step
-      for (int st = 0; st < p.n_bsteps; ++st) {
+      auto bsweep = [&](auto warp_only, int st0, int st1) {
+      constexpr bool kWarpOnly = decltype(warp_only)::value;
+      if (st0 >= st1) return;
+      uint64_t bd = h.bsched[st0 * G + gl];
+      uint64_t bd_next = h.bsched[min(st0 + 1, p.n_bsteps - 1) * G + gl];
+      OwnB own = load_own(bd);
+      for (int st = st0; st < st1; ++st) {
         const uint64_t bd_next2 = h.bsched[max(0, min(st + 2, p.n_bsteps - 1)) * G + gl];
         const unsigned bfl = static_cast<unsigned>(bd >> 32);
         double2* nd = s.node(static_cast<int>(bd & 0xFFFFu));
-        grp_sync<G>(gidx);                                    // the previous step's dx are visible
+        if (kWarpOnly) __syncwarp(); else grp_sync<G>(gidx);  // the previous step's dx are visible
         double2 xp = xl;
         if (!(bfl & kBschedRegParent)) xp = s.node(static_cast<int>((bd >> 16) & 0xFFFFu))[A_R];
         const OwnB own_next = load_own(bd_next);         // D^-1 J and D^-1 r are final since the forward sweep
@@ -462,6 +481,14 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
         if (!(bfl & kBschedIdle)) nd[A_R] = x;           // idle lanes (trash record) store nothing
         xl = x;
         bd = bd_next; bd_next = bd_next2; own = own_next;
+      }
+      };
+      if constexpr (G <= 32) {
+        bsweep(std::false_type{}, 0, p.n_bsteps);
+      } else {                                             // the levels below the roots fit one warp: warp 0 alone, then everybody
+        if ((gl >> 5) == 0) bsweep(std::true_type{}, 0, p.n_narrow_b);
+        if (p.n_narrow_b > 0 && p.n_narrow_b < p.n_bsteps) grp_sync<G>(gidx);
+        bsweep(std::false_type{}, p.n_narrow_b, p.n_bsteps);
       }
       grp_sync<G>(gidx);
     }

@@ -71,6 +71,7 @@ struct Params {
   // ---- sizes ----
   int n_bus, npq, n_load, n_sgen, n_line, n_lev, obs_dim, state_dim, n_slack_adj, slack_bus;
   int n_esteps, n_bsteps, has_extra_children;   // schedule lengths (for the handle's G); any bus with > 2 children
+  int n_wide_e, n_narrow_b;                     // G > 32: forward steps >= n_wide_e and back steps < n_narrow_b occupy lanes 0..31 only
   int nb;                 // envs processed by this launch
   int helper_threads;     // MODE_STEP: threads of the helper warps behind the solver threads of a CTA
   int env_stride2;        // double2 elements of smem per env

@@ -491,11 +491,20 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   // stay in registers.
   const int trash = npq + 1;
   std::vector<uint64_t> esched, bsched;
+  int n_wide_e = 0, n_narrow_b = 0;      // G > 32: forward steps [n_wide_e, end) and back steps [0, n_narrow_b) use warp 0 only
   {
     std::vector<int> lane_of(npq, -1), step_of(npq, -1), reg_child(npq, -1), epos(npq, -1);
     int cur = 0;
+    // Multi-warp groups (G > 32): the levels near the roots hold a handful of buses. From the first level on after which no
+    // level is wider than a warp ("narrow suffix" of the forward sweep / "narrow prefix" of the back sweep) only warp 0 of
+    // the group works: those steps are packed into lanes 0..31 and synchronise with __syncwarp instead of a named barrier.
+    int first_narrow_lev = n_lev;
+    if (G > 32) { while (first_narrow_lev > 0 && elev[first_narrow_lev] - elev[first_narrow_lev - 1] <= 32) --first_narrow_lev; }
+    n_wide_e = -1;
     for (int l = 0; l < n_lev; ++l) {
       const int w = elev[l + 1] - elev[l], nst = (w + G - 1) / G;
+      const bool narrow = G > 32 && l >= first_narrow_lev;
+      if (narrow && n_wide_e < 0) n_wide_e = cur;
       std::vector<int> slot(static_cast<size_t>(nst) * G, -1), inh(npq, -1);
       std::vector<int> rest;
       for (int k = elev[l]; k < elev[l + 1]; ++k) {
@@ -503,7 +512,8 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
         int pick = -1;
         if (nchild[i] >= 1 && nchild[i] <= 2)
           for (int c = cfirst[i]; c < cfirst[i] + nchild[i]; ++c)
-            if (step_of[c] == cur - 1 && slot[lane_of[c]] < 0 && (pick < 0 || height[c] > height[pick])) pick = c;
+            if (step_of[c] == cur - 1 && slot[lane_of[c]] < 0 && (!narrow || lane_of[c] < 32) &&
+                (pick < 0 || height[c] > height[pick])) pick = c;
         if (pick >= 0) { slot[lane_of[pick]] = i; inh[i] = pick; }
         else rest.push_back(i);
       }
@@ -532,12 +542,17 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     // a bus stores its Schur update only if its parent will fetch it from shared memory
     for (int i = 0; i < npq; ++i)
       if (parent[i] >= 0 && reg_child[parent[i]] != i) esched[epos[i]] |= static_cast<uint64_t>(kEschedStore) << 48;
+    if (n_wide_e < 0) n_wide_e = cur;             // no narrow suffix
     // back sweep by depth: children inherit the lane of their parent (the child with the tallest subtree first)
     std::fill(lane_of.begin(), lane_of.end(), -1); std::fill(step_of.begin(), step_of.end(), -1);
     cur = 0;
     const int first_back_level = 1;      // the roots' dx = D^-1 r is already in place
+    int last_narrow_dlev = first_back_level - 1;  // depth levels first_back_level .. last_narrow_dlev are narrow (prefix)
+    if (G > 32) { while (last_narrow_dlev + 1 < n_lev && dlev[last_narrow_dlev + 2] - dlev[last_narrow_dlev + 1] <= 32) ++last_narrow_dlev; }
+    n_narrow_b = 0;
     for (int l = first_back_level; l < n_lev; ++l) {
       const int w = dlev[l + 1] - dlev[l], nst = (w + G - 1) / G;
+      if (G > 32 && l <= last_narrow_dlev) n_narrow_b = cur + nst;
       std::vector<int> slot(static_cast<size_t>(nst) * G, -1);
       std::vector<char> reg(npq, 0);
       std::vector<int> nodes;
@@ -983,6 +998,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   P.n_bus = n; P.npq = npq; P.n_load = nl; P.n_sgen = ng; P.n_line = n_line; P.n_lev = n_lev;
   P.obs_dim = obs_dim; P.state_dim = state_dim; P.n_slack_adj = static_cast<int>(sl_node.size());
   P.n_esteps = n_esteps; P.n_bsteps = n_bsteps; P.has_extra_children = max_children > 2;
+  P.n_wide_e = std::min(n_wide_e, n_esteps); P.n_narrow_b = std::min(n_narrow_b, n_bsteps);
   P.slack_bus = slack;
   P.nb = cfg->batch; P.env_stride2 = stride2; P.pvq_off2 = pvq_off2; P.scratch_off2 = scratch_off2; P.hot_layout = hl;
   P.helper_off = hl.bytes + e->epb * stride2 * 16;
