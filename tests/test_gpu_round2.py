@@ -265,3 +265,23 @@ def test_node_relabelling_changes_addresses_not_results(monkeypatch):
         r0, t0, i0 = e0.step(a); r1, t1, i1 = e1.step(a)
         assert torch.equal(r0, r1) and torch.equal(t0, t1) and torch.equal(i0, i1) and torch.equal(e0.obs, e1.obs)
         assert torch.equal(e0.get_field("vm"), e1.get_field("vm")) and torch.equal(e0.get_state(), e1.get_state())
+
+
+def test_droop_on_a_meshed_net_uses_the_dense_solver():
+    """MODE_DROOP is instantiated for the dense-LU fallback too: same loop, same results as the host-driven loop."""
+    from mapdn_b200.baselines import droop_control, droop_control_host_loop
+    z = np.array([0.02 + 0.04j, 0.01 + 0.03j, 0.0125 + 0.025j, 0.015 + 0.03j])
+    net = NetDesc(base_mva=100.0, n_bus=4, slack_bus=0, slack_vm=1.03, br_from=np.array([0, 0, 1, 2]), br_to=np.array([1, 2, 2, 3]),
+                  br_r=z.real, br_x=z.imag, load_bus=np.array([1, 2, 3]), sgen_bus=np.array([2, 3]), sgen_zone=np.array([1, 1]),
+                  bus_zone=np.array([0, 1, 1, 1]), name="mesh4")
+    env = _make(net, None, None, batch=1)
+    assert env.dims["n_levels"] == 1                                   # meshed: no elimination forest
+    rng = np.random.default_rng(2)
+    B = 9
+    pl = rng.uniform(80, 260, (B, 3)); ql = pl * rng.uniform(0.2, 0.5, (B, 3))
+    pv = rng.uniform(0, 60, (B, 2)); s_rated = np.array([80.0, 80.0])
+    out = droop_control(env, pl, ql, pv, s_rated)
+    ref = droop_control_host_loop(env, pl, ql, pv, s_rated)
+    torch.cuda.synchronize()
+    assert torch.equal(out["iterations"], ref["iterations"]) and int(out["iterations"].max()) > 2
+    assert float((out["vm"] - ref["vm"]).abs().max()) < 1e-10 and float((out["q"] - ref["q"]).abs().max()) < 1e-8
