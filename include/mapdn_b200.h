@@ -210,6 +210,21 @@ mapdn_status mapdn_step_host_pinned(mapdn_env* env, const double* actions_host, 
 mapdn_status mapdn_wait(mapdn_env* env, void* stream);
 
 /*
+ * Host path with compact observation rows. get_obs (reference :232-316) pads every agent's row with zeros up to the
+ * longest one (:270-274); here the host receives obs_host [B, row_len] (double, or float when obs_is_f32) in which agent a
+ * owns entries [agent_off[a], agent_off[a] + agent_len[a]) - its reference row without the padding (row_len = sum of
+ * the lengths, rounded up to a multiple of 4 with zeros). The kernel writes the compact rows into device memory and ONE
+ * contiguous copy-engine transfer moves them (measured 55 GB/s, against 37 GB/s for the kernel's own posted writes of
+ * mapdn_step_host_pinned); actions are read from and reward / terminated / info written to host memory directly. All
+ * host buffers must be page-locked. sync as in mapdn_step_host_pinned.
+ */
+mapdn_status mapdn_obs_compact_layout(const mapdn_env* env, int32_t* agent_off /*[n_agents]*/,
+                                      int32_t* agent_len /*[n_agents]*/, int32_t* row_len);
+mapdn_status mapdn_step_host_compact(mapdn_env* env, const double* actions_host, int32_t add_noise,
+                                     double* reward_host, uint8_t* terminated_host, double* info_host,
+                                     void* obs_host, int32_t obs_is_f32, int32_t sync, void* stream);
+
+/*
  * Variants that deliver the observations in fp32 - what the reference's learners consume (prep_obs casts to
  * float32 right away, reference utilities/util.py:137-147). Halves the device->host traffic of the host-buffer
  * path; everything else (reward, info, the env state itself) stays fp64.

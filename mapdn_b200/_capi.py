@@ -67,7 +67,7 @@ class DimsC(C.Structure):
 
 
 EXPORTS = ("mapdn_abi_version", "mapdn_last_error", "mapdn_create", "mapdn_destroy", "mapdn_get_dims",
-           "mapdn_reset", "mapdn_step", "mapdn_step_host", "mapdn_step_f32obs", "mapdn_step_host_f32obs", "mapdn_step_host_pinned", "mapdn_wait", "mapdn_get_obs", "mapdn_get_state",
+           "mapdn_reset", "mapdn_step", "mapdn_step_host", "mapdn_step_f32obs", "mapdn_step_host_f32obs", "mapdn_step_host_pinned", "mapdn_wait", "mapdn_obs_compact_layout", "mapdn_step_host_compact", "mapdn_get_obs", "mapdn_get_state",
            "mapdn_get_field", "mapdn_solve", "mapdn_droop", "mapdn_get_ybus_dense", "mapdn_launch_count")
 
 _lib: Optional[C.CDLL] = None
@@ -103,6 +103,8 @@ def lib() -> C.CDLL:
         L.mapdn_step_host_pinned.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]
         L.mapdn_wait.argtypes = [vp, vp]
         L.mapdn_droop.argtypes = [vp, C.c_int32] + [vp] * 5 + [C.c_double, C.c_double, C.c_int32] + [vp] * 5
+        L.mapdn_obs_compact_layout.argtypes = [vp, vp, vp, vp]
+        L.mapdn_step_host_compact.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, C.c_int32, C.c_int32, vp]
     except AttributeError:
         if not dev_override:
             raise

@@ -1143,7 +1143,8 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
     // instruction writes 128 contiguous bytes per env (full lines when the destination is pinned host memory).
     // obs_skip_off: entries reading that slot (the padding) are not stored.
     if ((p.obs != nullptr || (MODE == MODE_STEP && p.obs32 != nullptr)) && valid) {
-      const int tot = ng * p.obs_dim;
+      const bool compact = p.obs_compact_len > 0;          // rows without the per-agent padding (staged host path)
+      const int tot = compact ? p.obs_compact_len : ng * p.obs_dim;
       const int skip = p.obs_skip_off;
       auto gather = [&](const uint16_t* __restrict__ prog, auto cold) {   // prog: shared (blob) or global (cold copy: read-only path)
         constexpr bool kCold = decltype(cold)::value;
@@ -1193,8 +1194,8 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
           }
         }
       };
-      if (h.in_blob) gather(reinterpret_cast<const uint16_t*>(smem_raw + hl.obs_off), std::false_type{});
-      else gather(p.obs_off, std::true_type{});
+      if (h.in_blob && !compact) gather(reinterpret_cast<const uint16_t*>(smem_raw + hl.obs_off), std::false_type{});
+      else gather(compact ? p.obs_compact_prog : p.obs_off, std::true_type{});
     }
     if (MODE == MODE_RESET && p.state != nullptr) {
       // get_state (:213-230): [P_bus | Q_bus | pv | q | vm | va(deg)] restricted to state_space (cold program)

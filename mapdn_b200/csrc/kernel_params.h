@@ -124,6 +124,8 @@ struct Params {
   float* obs32;           // alternative fp32 destination of the observations (MODE_STEP)
   int obs_skip_off;       // slab offset whose obs entries are NOT stored: -1 (store everything) or the zero slot (host
                           // path into a buffer whose padding is already zero: a third fewer bytes over PCIe)
+  const uint16_t* obs_compact_prog;  // the same program without the per-agent zero padding (rows of obs_compact_len entries)
+  int obs_compact_len;    // > 0: observations are written as compact rows (mapdn_step_host_compact); 0: padded layout
   double* dense_ws;       // meshed nets only: per resident env group, (2 npq) x (2 npq + 1) doubles [J | rhs]
   int dense_stride;       // doubles per group in dense_ws
   long long* prof;        // MAPDN_PROFILE builds: per-phase clock64 totals of warp 0 of block 0

@@ -170,6 +170,8 @@ struct mapdn_env {
   double *d_stage_actions = nullptr, *d_stage_reward = nullptr, *d_stage_info = nullptr, *d_stage_obs = nullptr;
   unsigned char* d_stage_term = nullptr;
   int obs_zero_off = 0;                // slab offset of the constant-zero slot the obs padding reads
+  std::vector<int> agent_len, agent_off;   // compact observation rows: true length / offset of every agent's block
+  int compact_row = 0;                 // entries per compact row (sum of agent_len, rounded up to a multiple of 4)
   std::vector<const void*> pinned_ok;  // host buffers already verified as pinned (mapdn_step_host_pinned)
 };
 
@@ -763,6 +765,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   std::vector<uint16_t> obs_off(static_cast<size_t>(ng) * obs_dim);
   std::vector<unsigned> obs_src(static_cast<size_t>(ng) * obs_dim, 0u);
   std::vector<int> obs_xptr(static_cast<size_t>(ng) * obs_dim + 1, 0), obs_xidx;
+  std::vector<int> agent_len(ng, 0);
   enum { K_ZERO = 0, K_P = 1, K_Q = 2, K_PV = 3, K_QSG = 4, K_VM = 5, K_VA = 6 };
   for (int a = 0; a < ng; ++a) {
     // entry list of this agent in the reference's order (:254-266), then zero padding (:270-274)
@@ -772,6 +775,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     if (ss_q) ent.push_back({K_QSG, a});
     if (ss_vm) for (int b : zb[a]) ent.push_back({K_VM, b});
     if (ss_va) for (int b : zb[a]) ent.push_back({K_VA, b});
+    agent_len[a] = static_cast<int>(ent.size());
     for (int k = 0; k < obs_dim; ++k) {
       const size_t idx = static_cast<size_t>(a) * obs_dim + k;
       obs_xptr[idx] = static_cast<int>(obs_xidx.size());
@@ -794,6 +798,15 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     }
   }
   obs_xptr[static_cast<size_t>(ng) * obs_dim] = static_cast<int>(obs_xidx.size());
+  // the same program without the padding: agent blocks back to back, the row rounded up to 4 entries (16-byte pieces of
+  // fp32 rows) with reads of the zero slot
+  std::vector<uint16_t> obs_compact;
+  std::vector<int> agent_off(ng, 0);
+  for (int a = 0; a < ng; ++a) {
+    agent_off[a] = static_cast<int>(obs_compact.size());
+    for (int k = 0; k < agent_len[a]; ++k) obs_compact.push_back(obs_off[static_cast<size_t>(a) * obs_dim + k]);
+  }
+  while (obs_compact.size() % 4) obs_compact.push_back(static_cast<uint16_t>(2 * (npq * kNodeArrays2 + A_UP)));
   // state program (reference get_state :213-230), bus-indexed
   std::vector<unsigned> state_src;
   if (ss_dem) { for (int b = 0; b < n; ++b) state_src.push_back((7u << 28) | b); for (int b = 0; b < n; ++b) state_src.push_back((8u << 28) | b); }
@@ -1005,6 +1018,9 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   P.stage_in_records = stage_rec ? 1 : 0;
   P.obs_skip_off = -1;
   e->obs_zero_off = 2 * (npq * kNodeArrays2 + A_UP);
+  TRY(dev_upload(e, obs_compact, &P.obs_compact_prog));
+  P.obs_compact_len = 0;
+  e->agent_len = agent_len; e->agent_off = agent_off; e->compact_row = static_cast<int>(obs_compact.size());
   {   // bus shunts by node (res_bus p/q carry the shunt power, pandapower _get_shunt_results)
     std::vector<double> sh_g(npq + 1), sh_b(npq + 1);
     bool any = false;
@@ -1187,6 +1203,44 @@ mapdn_status mapdn_step_host_pinned(mapdn_env* e, const double* actions_host, in
   s = launch_env_kernel(e, MODE_STEP, p, static_cast<cudaStream_t>(stream));
   if (s != MAPDN_OK) return s;
   if (sync) MAPDN_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  return MAPDN_OK;
+}
+
+mapdn_status mapdn_obs_compact_layout(const mapdn_env* e, int32_t* agent_off, int32_t* agent_len, int32_t* row_len) {
+  if (!e) return fail(MAPDN_ERR_INVALID, "null handle");
+  for (int a = 0; a < e->dims.n_agents; ++a) {
+    if (agent_off) agent_off[a] = e->agent_off[a];
+    if (agent_len) agent_len[a] = e->agent_len[a];
+  }
+  if (row_len) *row_len = e->compact_row;
+  return MAPDN_OK;
+}
+
+mapdn_status mapdn_step_host_compact(mapdn_env* e, const double* actions_host, int32_t add_noise, double* reward_host,
+                                     uint8_t* terminated_host, double* info_host, void* obs_host, int32_t obs_is_f32,
+                                     int32_t sync, void* stream) {
+  if (!e || !actions_host || !reward_host || !terminated_host || !obs_host) return fail(MAPDN_ERR_INVALID, "null argument");
+  if (!e->base.prof_pv) return fail(MAPDN_ERR_INVALID, "handle was created without a profile store");
+  MAPDN_ON_DEVICE(e->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  void *a, *r, *t, *i, *o;
+  mapdn_status s;
+  if ((s = pinned_alias(e, actions_host, &a, "actions_host")) != MAPDN_OK) return s;
+  if ((s = pinned_alias(e, reward_host, &r, "reward_host")) != MAPDN_OK) return s;
+  if ((s = pinned_alias(e, terminated_host, &t, "terminated_host")) != MAPDN_OK) return s;
+  if ((s = pinned_alias(e, info_host, &i, "info_host")) != MAPDN_OK) return s;
+  if ((s = pinned_alias(e, obs_host, &o, "obs_host")) != MAPDN_OK) return s;    // pageable memory would make the copy synchronous
+  Params p = e->base;
+  p.actions = static_cast<const double*>(a); p.add_noise = add_noise; p.reward = static_cast<double*>(r);
+  p.term = static_cast<unsigned char*>(t); p.info = static_cast<double*>(i);
+  p.obs = obs_is_f32 ? nullptr : e->d_stage_obs;                      // compact rows are narrower than the padded ones
+  p.obs32 = obs_is_f32 ? reinterpret_cast<float*>(e->d_stage_obs) : nullptr;
+  p.obs_compact_len = e->compact_row;
+  s = launch_env_kernel(e, MODE_STEP, p, st);
+  if (s != MAPDN_OK) return s;
+  const size_t bytes = static_cast<size_t>(e->dims.batch) * e->compact_row * (obs_is_f32 ? sizeof(float) : sizeof(double));
+  MAPDN_CUDA(cudaMemcpyAsync(obs_host, e->d_stage_obs, bytes, cudaMemcpyDeviceToHost, st));
+  if (sync) MAPDN_CUDA(cudaStreamSynchronize(st));
   return MAPDN_OK;
 }
 

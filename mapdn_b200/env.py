@@ -222,19 +222,39 @@ class BatchedVoltageControl:
         return self._host
 
     def step_host(self, actions: np.ndarray, add_noise: bool = True, obs_dtype=np.float64, staged: bool = False,
-                  sync: bool = True):
+                  sync: bool = True, layout: str = "padded"):
         """NumPy in / NumPy out. Default: the zero-copy path (``mapdn_step_host_pinned``) - the fused kernel reads the
         actions from and writes reward / terminated / info / observations straight to this object's pinned host
         buffers, so the PCIe transfer overlaps the kernel; the never-changing zero padding of the observation rows is
         not rewritten. ``staged=True``: the round-1 path (H2D copy, kernel, four D2H copies). ``obs_dtype=np.float32``
         delivers the observations in fp32 (what the reference's learners use after ``prep_obs``). ``sync=False`` returns
         right after the launch - call :meth:`wait` before reading the results. Returns views of pinned host buffers
-        (overwritten by the next call)."""
+        (overwritten by the next call).
+
+        ``layout="compact"`` (``mapdn_step_host_compact``): the observations arrive as rows ``[B, row_len]`` without the
+        zero padding of the reference's ``get_obs`` - agent ``a`` owns ``obs[:, off:off + n]`` with ``(off, n) =
+        self.obs_slices[a]`` (a strided NumPy view, no copy; :meth:`expand_obs` rebuilds the padded array). The rows
+        go through device memory and ONE contiguous copy-engine transfer, which is faster than the kernel's own posted
+        writes over PCIe (55 against 37 GB/s measured)."""
         hb = self._host_buffers()
         hb["actions"].numpy()[...] = actions
         f32 = np.dtype(obs_dtype) == np.float32
-        obs = hb["obs32"] if f32 else hb["obs"]
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        if layout == "compact":
+            if self.history > 1:
+                raise NotImplementedError("compact host rows carry one frame (history = 1)")
+            row = self.obs_row_len
+            key = "obs_c32" if f32 else "obs_c"
+            if key not in hb:
+                hb[key] = torch.zeros(self.batch, row, dtype=torch.float32 if f32 else torch.float64).pin_memory()
+            obs = hb[key]
+            _capi.check(self._L.mapdn_step_host_compact(self._h, hb["actions"].data_ptr(), int(add_noise),
+                                                        hb["reward"].data_ptr(), hb["terminated"].data_ptr(),
+                                                        hb["info"].data_ptr(), obs.data_ptr(), int(f32), int(sync), stream))
+            return hb["reward"].numpy(), hb["terminated"].numpy(), hb["info"].numpy(), obs.numpy()
+        if layout != "padded":
+            raise ValueError("layout must be 'padded' or 'compact'")
+        obs = hb["obs32"] if f32 else hb["obs"]
         if staged:
             fn = self._L.mapdn_step_host_f32obs if f32 else self._L.mapdn_step_host
             _capi.check(fn(self._h, hb["actions"].data_ptr(), int(add_noise), hb["reward"].data_ptr(),
@@ -248,6 +268,33 @@ class BatchedVoltageControl:
     def wait(self):
         """Blocks until the results of a ``step_host(..., sync=False)`` are in the host buffers."""
         _capi.check(self._L.mapdn_wait(self._h, torch.cuda.current_stream(self.device).cuda_stream))
+
+    def _compact_layout(self):
+        if getattr(self, "_obs_slices", None) is None:
+            off = (C.c_int32 * self.n_agents)()
+            ln = (C.c_int32 * self.n_agents)()
+            row = C.c_int32(0)
+            _capi.check(self._L.mapdn_obs_compact_layout(self._h, off, ln, C.byref(row)))
+            self._obs_slices = [(int(off[a]), int(ln[a])) for a in range(self.n_agents)]
+            self._obs_row_len = int(row.value)
+        return self._obs_slices, self._obs_row_len
+
+    @property
+    def obs_slices(self):
+        """``[(offset, length)]`` of every agent's block in a compact observation row (``step_host(layout="compact")``)."""
+        return self._compact_layout()[0]
+
+    @property
+    def obs_row_len(self) -> int:
+        return self._compact_layout()[1]
+
+    def expand_obs(self, compact: np.ndarray) -> np.ndarray:
+        """Compact rows ``[B, row_len]`` -> the reference's padded ``[B, n_agents, obs_dim]`` (a host-side copy: for checks
+        and for consumers that insist on the padded layout)."""
+        out = np.zeros((compact.shape[0], self.n_agents, self.obs_size), dtype=compact.dtype)
+        for a, (off, n) in enumerate(self.obs_slices):
+            out[:, a, :n] = compact[:, off:off + n]
+        return out
 
     @property
     def host_obs_bytes_per_env(self) -> int:

@@ -285,3 +285,61 @@ def test_droop_on_a_meshed_net_uses_the_dense_solver():
     torch.cuda.synchronize()
     assert torch.equal(out["iterations"], ref["iterations"]) and int(out["iterations"].max()) > 2
     assert float((out["vm"] - ref["vm"]).abs().max()) < 1e-10 and float((out["q"] - ref["q"]).abs().max()) < 1e-8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scenario,batch", [("case33", 37), ("case141", 9), ("case322", 5)])
+def test_compact_host_rows_equal_the_padded_observations(scenario, batch):
+    """mapdn_step_host_compact: agent a's block of a compact row == its reference row without the zero padding
+    (voltage_control_env.py:254-274); the padded layout is rebuilt exactly by expand_obs; fp32 rows are the rounded
+    fp64 ones."""
+    from mapdn_b200 import cases
+    from mapdn_b200.env import BatchedVoltageControl
+    net, prof = cases.make_case(scenario), cases.make_profiles(scenario, n_days=3)
+    mk = lambda: BatchedVoltageControl(net, prof, dict(seed=11), batch=batch)
+    a, b, c = mk(), mk(), mk()
+    for e in (a, b, c):
+        e.reset()
+    slices = a.obs_slices
+    assert len(slices) == a.n_agents and a.obs_row_len % 4 == 0
+    assert sum(n for _, n in slices) <= a.obs_row_len < sum(n for _, n in slices) + 4
+    assert a.host_obs_bytes_per_env == 8 * sum(n for _, n in slices)
+    rng = np.random.default_rng(5)
+    for t in range(3):
+        act = rng.uniform(-0.8, 0.8, (batch, a.n_agents))
+        r0, d0, i0, o0 = [x.copy() for x in a.step_host(act, add_noise=True)]
+        r1, d1, i1, o1 = [x.copy() for x in b.step_host(act, add_noise=True, layout="compact")]
+        r2, d2, i2, o2 = [x.copy() for x in c.step_host(act, add_noise=True, layout="compact", obs_dtype=np.float32)]
+        assert o1.shape == (batch, a.obs_row_len) and o2.dtype == np.float32
+        np.testing.assert_array_equal(r0, r1); np.testing.assert_array_equal(d0, d1); np.testing.assert_array_equal(i0, i1)
+        np.testing.assert_array_equal(r0, r2)
+        np.testing.assert_array_equal(a.expand_obs(o1), o0)                       # bit-exact, padding included
+        np.testing.assert_array_equal(a.expand_obs(o2), o0.astype(np.float32))
+        for ag, (off, n) in enumerate(slices):
+            assert not np.any(o0[:, ag, n:])                                      # what is left out is zero padding
+        np.testing.assert_array_equal(o1[:, sum(n for _, n in slices):], 0.0)     # row tail
+    # non-blocking form
+    act = rng.uniform(-0.8, 0.8, (batch, a.n_agents))
+    ref = [x.copy() for x in a.step_host(act)]
+    out = b.step_host(act, layout="compact", sync=False)
+    b.wait()
+    np.testing.assert_array_equal(a.expand_obs(out[3]), ref[3])
+    for e in (a, b, c):
+        e.close()
+
+
+@pytest.mark.gpu
+def test_compact_host_path_rejects_pageable_memory():
+    import ctypes as C
+    from mapdn_b200 import cases, _capi
+    from mapdn_b200.env import BatchedVoltageControl
+    net, prof = cases.make_case("case33"), cases.make_profiles("case33", n_days=3)
+    env = BatchedVoltageControl(net, prof, dict(seed=1), batch=4)
+    env.reset()
+    hb = env._host_buffers()
+    pageable = np.zeros((4, env.obs_row_len))
+    st = env._L.mapdn_step_host_compact(env._h, hb["actions"].data_ptr(), 1, hb["reward"].data_ptr(),
+                                        hb["terminated"].data_ptr(), hb["info"].data_ptr(),
+                                        pageable.ctypes.data, 0, 1, None)
+    assert st != 0 and b"obs_host" in env._L.mapdn_last_error()
+    env.close()
