@@ -411,7 +411,7 @@ def measure(sc, barrier, global_batch, K, W, Ke, tm, local, rank, flush, lanes=0
     host_acts = [rng.uniform(lo, hi, (B, env.n_agents)) for _ in range(4)]
     for tag in obs_dtypes:
         odt = np.float32 if tag in ("f32", "compact_f32") else np.float64
-        staged = tag == "staged"
+        staged = {"staged": True, "compact_zc_f64": False}.get(tag)      # None: the layout's default path
         layout = "compact" if tag.startswith("compact") else "padded"
         env.reset(); state["t"] = 0
         for i in range(3):
@@ -425,19 +425,21 @@ def measure(sc, barrier, global_batch, K, W, Ke, tm, local, rank, flush, lanes=0
             state["t"] += 1
         tm.sync_all()
         dt = tm.max_over_ranks(time.perf_counter() - e0)
-        if staged:
-            obs_bytes = env.n_agents * env.obs_size * 8
-        elif layout == "compact":
+        if layout == "compact":
             obs_bytes = env.obs_row_len * (4 if odt is np.float32 else 8)
+        elif staged:
+            obs_bytes = env.n_agents * env.obs_size * 8
         else:
             obs_bytes = env.host_obs_bytes_per_env // (2 if tag == "f32" else 1)
         out[{"f64": "e2e", "f32": "e2e_obs_f32", "staged": "e2e_staged", "compact_f64": "e2e_compact",
-             "compact_f32": "e2e_compact_f32"}[tag]] = dict(
+             "compact_f32": "e2e_compact_f32", "compact_zc_f64": "e2e_compact_zero_copy"}[tag]] = dict(
             value=global_batch * Ke / dt, unit="env-steps/s", h2d_bytes_per_step=B * env.n_agents * 8,
             d2h_bytes_per_step=B * (8 + 1 + 11 * 8 + obs_bytes), steps=Ke, obs_dtype="f32" if odt is np.float32 else "f64",
-            path="staged copies: H2D actions, kernel, 4 x D2H (full padded obs rows)" if staged else
-                 "compact rows [B, sum of the agents' true lengths] (no zero padding): kernel -> device rows -> ONE "
-                 "copy-engine D2H; actions / reward / terminated / info zero-copy" if layout == "compact" else
+            path="compact rows [B, sum of the agents' true lengths] (no zero padding): kernel -> device rows -> ONE "
+                 "copy-engine D2H; actions / reward / terminated / info zero-copy" if layout == "compact" and staged is None else
+                 "compact rows [B, sum of the agents' true lengths] (no zero padding), zero-copy like the padded path"
+                 if layout == "compact" else
+                 "staged copies: H2D actions, kernel, 4 x D2H (full padded obs rows)" if staged else
                  "zero-copy: the kernel reads actions from / writes results to pinned host memory; obs padding "
                  "(constant zeros) not rewritten")
     env.close()
@@ -523,7 +525,7 @@ def run_ours(args):
         parity = parity_check(sc, barrier, B, local)
     clocks = ClockSampler(local) if rank == 0 else None
     m = measure(sc, barrier, B * world, K, W, Ke, tm, local, rank, flush, lanes=args.lanes, clocks=clocks,
-                obs_dtypes=("f64", "f32", "staged", "compact_f64", "compact_f32"), min_warm=50)
+                obs_dtypes=("f64", "f32", "staged", "compact_f64", "compact_f32", "compact_zc_f64"), min_warm=50)
 
     # ---- the other BASELINE.json configurations of this GPU count ----
     subs = []
@@ -596,6 +598,8 @@ def run_ours(args):
                 e2e_compact=dict(m["e2e_compact"], note="opt-in host layout without the reference's zero padding "
                                                         "(step_host(layout='compact'), mapdn_step_host_compact)"),
                 e2e_compact_f32=dict(m["e2e_compact_f32"], note="compact rows in fp32"),
+                e2e_compact_zero_copy=dict(m["e2e_compact_zero_copy"], note="compact rows written by the kernel itself "
+                                           "(step_host(layout='compact', staged=False))"),
                 roofline=roofline, cpu_baseline=cpu, wall_ms_per_step=m["wall_ms_per_step"],
                 newton_iters_mean=m["newton_iters_mean"], nonconverged_frac=m["nonconverged_frac"],
                 side_metrics_note="Newton iterations / diverged fraction of the last timed step, mean over the batch",

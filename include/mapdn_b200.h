@@ -216,13 +216,16 @@ mapdn_status mapdn_wait(mapdn_env* env, void* stream);
  * the lengths, rounded up to a multiple of 4 with zeros). The kernel writes the compact rows into device memory and ONE
  * contiguous copy-engine transfer moves them (measured 55 GB/s, against 37 GB/s for the kernel's own posted writes of
  * mapdn_step_host_pinned); actions are read from and reward / terminated / info written to host memory directly. All
- * host buffers must be page-locked. sync as in mapdn_step_host_pinned.
+ * host buffers must be page-locked. direct = 1: the kernel writes the compact rows to obs_host itself instead (no
+ * device staging, no copy; contiguous rows reach 43 GB/s, measured 5 % slower end to end than the copy). sync as in
+ * mapdn_step_host_pinned.
  */
 mapdn_status mapdn_obs_compact_layout(const mapdn_env* env, int32_t* agent_off /*[n_agents]*/,
                                       int32_t* agent_len /*[n_agents]*/, int32_t* row_len);
 mapdn_status mapdn_step_host_compact(mapdn_env* env, const double* actions_host, int32_t add_noise,
                                      double* reward_host, uint8_t* terminated_host, double* info_host,
-                                     void* obs_host, int32_t obs_is_f32, int32_t sync, void* stream);
+                                     void* obs_host, int32_t obs_is_f32, int32_t direct, int32_t sync,
+                                     void* stream);
 
 /*
  * Variants that deliver the observations in fp32 - what the reference's learners consume (prep_obs casts to

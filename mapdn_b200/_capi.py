@@ -104,7 +104,7 @@ def lib() -> C.CDLL:
         L.mapdn_wait.argtypes = [vp, vp]
         L.mapdn_droop.argtypes = [vp, C.c_int32] + [vp] * 5 + [C.c_double, C.c_double, C.c_int32] + [vp] * 5
         L.mapdn_obs_compact_layout.argtypes = [vp, vp, vp, vp]
-        L.mapdn_step_host_compact.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, C.c_int32, C.c_int32, vp]
+        L.mapdn_step_host_compact.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]
     except AttributeError:
         if not dev_override:
             raise

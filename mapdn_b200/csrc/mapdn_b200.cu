@@ -1218,7 +1218,7 @@ mapdn_status mapdn_obs_compact_layout(const mapdn_env* e, int32_t* agent_off, in
 
 mapdn_status mapdn_step_host_compact(mapdn_env* e, const double* actions_host, int32_t add_noise, double* reward_host,
                                      uint8_t* terminated_host, double* info_host, void* obs_host, int32_t obs_is_f32,
-                                     int32_t sync, void* stream) {
+                                     int32_t direct, int32_t sync, void* stream) {
   if (!e || !actions_host || !reward_host || !terminated_host || !obs_host) return fail(MAPDN_ERR_INVALID, "null argument");
   if (!e->base.prof_pv) return fail(MAPDN_ERR_INVALID, "handle was created without a profile store");
   MAPDN_ON_DEVICE(e->device);
@@ -1233,13 +1233,16 @@ mapdn_status mapdn_step_host_compact(mapdn_env* e, const double* actions_host, i
   Params p = e->base;
   p.actions = static_cast<const double*>(a); p.add_noise = add_noise; p.reward = static_cast<double*>(r);
   p.term = static_cast<unsigned char*>(t); p.info = static_cast<double*>(i);
-  p.obs = obs_is_f32 ? nullptr : e->d_stage_obs;                      // compact rows are narrower than the padded ones
-  p.obs32 = obs_is_f32 ? reinterpret_cast<float*>(e->d_stage_obs) : nullptr;
+  void* dst = direct ? o : static_cast<void*>(e->d_stage_obs);       // compact rows are narrower than the padded ones
+  p.obs = obs_is_f32 ? nullptr : static_cast<double*>(dst);
+  p.obs32 = obs_is_f32 ? static_cast<float*>(dst) : nullptr;
   p.obs_compact_len = e->compact_row;
   s = launch_env_kernel(e, MODE_STEP, p, st);
   if (s != MAPDN_OK) return s;
-  const size_t bytes = static_cast<size_t>(e->dims.batch) * e->compact_row * (obs_is_f32 ? sizeof(float) : sizeof(double));
-  MAPDN_CUDA(cudaMemcpyAsync(obs_host, e->d_stage_obs, bytes, cudaMemcpyDeviceToHost, st));
+  if (!direct) {
+    const size_t bytes = static_cast<size_t>(e->dims.batch) * e->compact_row * (obs_is_f32 ? sizeof(float) : sizeof(double));
+    MAPDN_CUDA(cudaMemcpyAsync(obs_host, e->d_stage_obs, bytes, cudaMemcpyDeviceToHost, st));
+  }
   if (sync) MAPDN_CUDA(cudaStreamSynchronize(st));
   return MAPDN_OK;
 }

@@ -308,8 +308,9 @@ def test_compact_host_rows_equal_the_padded_observations(scenario, batch):
     for t in range(3):
         act = rng.uniform(-0.8, 0.8, (batch, a.n_agents))
         r0, d0, i0, o0 = [x.copy() for x in a.step_host(act, add_noise=True)]
-        r1, d1, i1, o1 = [x.copy() for x in b.step_host(act, add_noise=True, layout="compact")]
-        r2, d2, i2, o2 = [x.copy() for x in c.step_host(act, add_noise=True, layout="compact", obs_dtype=np.float32)]
+        r1, d1, i1, o1 = [x.copy() for x in b.step_host(act, add_noise=True, layout="compact", staged=False if t & 1 else None)]
+        r2, d2, i2, o2 = [x.copy() for x in c.step_host(act, add_noise=True, layout="compact", obs_dtype=np.float32,
+                                                        staged=None if t & 1 else False)]
         assert o1.shape == (batch, a.obs_row_len) and o2.dtype == np.float32
         np.testing.assert_array_equal(r0, r1); np.testing.assert_array_equal(d0, d1); np.testing.assert_array_equal(i0, i1)
         np.testing.assert_array_equal(r0, r2)
@@ -340,6 +341,6 @@ def test_compact_host_path_rejects_pageable_memory():
     pageable = np.zeros((4, env.obs_row_len))
     st = env._L.mapdn_step_host_compact(env._h, hb["actions"].data_ptr(), 1, hb["reward"].data_ptr(),
                                         hb["terminated"].data_ptr(), hb["info"].data_ptr(),
-                                        pageable.ctypes.data, 0, 1, None)
+                                        pageable.ctypes.data, 0, 0, 1, None)
     assert st != 0 and b"obs_host" in env._L.mapdn_last_error()
     env.close()
