@@ -1100,7 +1100,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   }
   // staging for the *_host entry points
   TRY(dev_alloc(e, B * ng, &e->d_stage_actions)); TRY(dev_alloc(e, B, &e->d_stage_reward)); TRY(dev_alloc(e, B, &e->d_stage_term));
-  TRY(dev_alloc(e, B * MAPDN_N_INFO, &e->d_stage_info)); TRY(dev_alloc(e, B * ng * obs_dim, &e->d_stage_obs));
+  TRY(dev_alloc(e, B * MAPDN_N_INFO, &e->d_stage_info)); TRY(dev_alloc(e, B * std::max<size_t>(ng * obs_dim, e->compact_row), &e->d_stage_obs));   // compact rows round up to 4 entries
 
   mapdn_dims& d = e->dims;
   d.batch = cfg->batch; d.n_bus = n; d.n_branch = nbr; d.n_line = n_line; d.n_load = nl; d.n_sgen = ng;
@@ -1233,7 +1233,7 @@ mapdn_status mapdn_step_host_compact(mapdn_env* e, const double* actions_host, i
   Params p = e->base;
   p.actions = static_cast<const double*>(a); p.add_noise = add_noise; p.reward = static_cast<double*>(r);
   p.term = static_cast<unsigned char*>(t); p.info = static_cast<double*>(i);
-  void* dst = direct ? o : static_cast<void*>(e->d_stage_obs);       // compact rows are narrower than the padded ones
+  void* dst = direct ? o : static_cast<void*>(e->d_stage_obs);
   p.obs = obs_is_f32 ? nullptr : static_cast<double*>(dst);
   p.obs32 = obs_is_f32 ? static_cast<float*>(dst) : nullptr;
   p.obs_compact_len = e->compact_row;

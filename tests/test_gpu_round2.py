@@ -344,3 +344,28 @@ def test_compact_host_path_rejects_pageable_memory():
                                         pageable.ctypes.data, 0, 0, 1, None)
     assert st != 0 and b"obs_host" in env._L.mapdn_last_error()
     env.close()
+
+
+@pytest.mark.gpu
+def test_compact_rows_longer_than_the_padded_ones():
+    """One agent, 14 entries: no padding at all, and the compact row (rounded up to 16 entries) is LONGER than the padded
+    one - the device staging buffer has to be sized for it."""
+    net = NetDesc(base_mva=1.0, n_bus=4, slack_bus=0, slack_vm=1.0, br_from=np.array([0, 1, 1]), br_to=np.array([1, 2, 3]),
+                  br_r=np.array([0.01, 0.02, 0.015]), br_x=np.array([0.02, 0.03, 0.02]), load_bus=np.array([2, 3]),
+                  sgen_bus=np.array([3]), sgen_zone=np.array([1]), bus_zone=np.array([0, 1, 1, 1]), name="tiny4")
+    T = 3 * 480 + 1
+    rng = np.random.default_rng(0)
+    prof = ProfileDesc(pv=rng.uniform(0.1, 0.3, (T, 1)), load_p=rng.uniform(0.1, 0.4, (T, 2)),
+                       load_q=rng.uniform(0.0, 0.1, (T, 2)), steps_per_hour=20, n_days=3)
+    a, b = _make(net, prof, dict(seed=2), batch=7), _make(net, prof, dict(seed=2), batch=7)
+    a.reset(); b.reset()
+    assert a.obs_size == 14 and b.obs_slices == [(0, 14)] and b.obs_row_len == 16
+    for t in range(4):
+        act = rng.uniform(-0.8, 0.8, (7, 1))
+        ref = [x.copy() for x in a.step_host(act)]
+        out = [x.copy() for x in b.step_host(act, layout="compact", staged=False if t & 1 else None,
+                                             obs_dtype=np.float32 if t & 2 else np.float64)]
+        np.testing.assert_array_equal(out[0], ref[0])
+        np.testing.assert_array_equal(out[3][:, :14], ref[3][:, 0, :].astype(out[3].dtype))
+        np.testing.assert_array_equal(out[3][:, 14:], 0.0)
+    a.close(); b.close()
