@@ -6,6 +6,12 @@ Restated with the *intended* pandas-1.1.3 semantics of ``get_obs`` (the chained 
 at reference :239-244 mutates the zone frames there; under pandas 3 it is a no-op).
 Sequencing quirks follow SURVEY Appendix B. Randomness comes from ``oracle.philox_ref`` (the
 reference's global ``np.random`` stream cannot be reproduced by construction).
+
+PINNED: ``tests/test_reference_golden.py`` replays trajectories that the reference's own, unmodified
+``VoltageControl`` code produced in this container (``oracle/ref_harness.py``: substitute pandapower whose ``runpp`` is
+``PandapowerEquivalent``, pandas-1.1.3 table semantics, ``np.random`` fed with the Philox draws) and this class
+reproduces them to 1e-11 - reset incl. retries, noisy and noise-free steps, all barriers, ``line_weight``,
+``state_space`` subsets, the divergence branch.
 """
 from __future__ import annotations
 

@@ -162,10 +162,13 @@ def test_cuda_path_reproduces_the_reference_trajectories(name):
             torch.cuda.synchronize()
             live = np.nonzero(g["alive"][t])[0]
             sel = [ids[k] for k in live]
-            assert np.abs(r[sel].cpu().numpy() - g["reward"][t, live]).max() < 1e-9
-            assert np.array_equal(term[sel].cpu().numpy(), g["term"][t, live])
-            assert np.abs(info[sel].cpu().numpy() - g["info"][t, live]).max() < 1e-9
+            if live.size:
+                assert np.abs(r[sel].cpu().numpy() - g["reward"][t, live]).max() < 1e-9
+                assert np.array_equal(term[sel].cpu().numpy(), g["term"][t, live])
+                assert np.abs(info[sel].cpu().numpy() - g["info"][t, live]).max() < 1e-9
             t += 1
+            if live.size == 0:          # every env of the scenario has terminated (the reference's caller would reset)
+                continue
         else:
             if op[0] == "manual":
                 start = np.zeros((B, 3), np.int32)
@@ -184,4 +187,51 @@ def test_cuda_path_reproduces_the_reference_trajectories(name):
             sel = ids
         assert np.abs(env.obs[sel].cpu().numpy() - g["obs"][k_op, live]).max() < 1e-9
         assert np.abs(st[sel].cpu().numpy() - g["state"][k_op, live]).max() < 1e-8
+    env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", [n for n in NAMES if S.SCENARIOS[n]["env_ids"][0] == 0 and not n.startswith("case322")])
+def test_drop_in_class_reproduces_the_reference_trajectories(name):
+    """The same replay through ``mapdn_b200.VoltageControl`` - the class a user of the reference switches to (same
+    constructor argument, method names, NumPy shapes, info keys): it is env id 0 of the batched engine."""
+    from mapdn_b200.env import INFO_KEYS, VoltageControl
+    g, ops = _load(name)
+    sc = S.SCENARIOS[name]
+    net, prof = sc["build"]()
+    env = VoltageControl(dict(sc["args"], net=net, profiles=prof))          # resets like the reference's __init__ (:85)
+    nb, ng = net.n_bus, net.n_sgen
+    t = 0
+    for k_op, op in enumerate(ops):
+        if op[0] == "step":
+            if not g["alive"][t, 0]:
+                break
+            reward, terminated, info = env.step(g["actions"][t, 0], add_noise=op[1])
+            assert abs(reward - g["reward"][t, 0]) < 1e-9 and terminated == bool(g["term"][t, 0])
+            assert list(info) == list(INFO_KEYS)
+            assert np.abs(np.array([info[q] for q in INFO_KEYS]) - g["info"][t, 0]).max() < 1e-9
+            t += 1
+            obs, state = env.get_obs(), env.get_state()
+        elif op[0] == "init":
+            obs, state = env.get_obs(), env.get_state()
+        elif op[0] == "reset":
+            obs, state = env.reset()
+        else:
+            obs, state = env.manual_reset(*S.manual_of(sc, op, 0))
+        if op[0] != "step":
+            d, h, i = g["start"][sum(1 for o in ops[:k_op] if o[0] != "step"), 0]
+            assert (env._episode_start_day, env._episode_start_hour, env._episode_start_interval) == (d, h, i)
+            assert env.steps == 1 and env.sum_rewards == 0
+        assert isinstance(obs, list) and len(obs) == ng and obs[0].shape == (env.get_obs_size(),)
+        assert np.abs(np.array(obs) - g["obs"][k_op, 0]).max() < 1e-9
+        assert state.shape == (env.get_state_size(),) and np.abs(state - g["state"][k_op, 0]).max() < 1e-8
+        if "state_space" not in sc["args"]:          # default layout: [p_bus | q_bus | pv | q | vm | va_degree] (:213-230)
+            ref = g["state"][k_op, 0]
+            assert np.abs(env._get_res_bus_active() - ref[:nb]).max() < 1e-9
+            assert np.abs(env._get_res_bus_reactive() - ref[nb:2 * nb]).max() < 1e-9
+            assert np.abs(env._get_sgen_active() - ref[2 * nb:2 * nb + ng]).max() < 1e-9
+            assert np.abs(env._get_sgen_reactive() - ref[2 * nb + ng:2 * nb + 2 * ng]).max() < 1e-9
+            assert np.abs(env._get_res_bus_v() - ref[2 * nb + 2 * ng:3 * nb + 2 * ng]).max() < 1e-9
+    info_env = env.get_env_info()
+    assert info_env["n_agents"] == ng and info_env["obs_shape"] == g["obs"].shape[-1] and info_env["state_shape"] == g["state"].shape[-1]
     env.close()
