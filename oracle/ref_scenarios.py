@@ -109,6 +109,10 @@ _add("case33_state_space", lambda: _case("case33"),
      dict(voltage_barrier_type="bowl", action_scale=0.8, seed=8, state_space=["pv", "vm_pu", "demand"], reset_action=False,
           voltage_weight=2.5, q_weight=0.3, v_upper=1.03, v_lower=0.97, episode_limit=6), (0, 5),
      [("init",)] + [("step", True)] * 5)          # steps reaches episode_limit: terminated without divergence
+# obs history (:303-315): every get_obs() call stacks the last `history` frames (zero frames first); the fixtures hold the
+# stacked rows, the batched engine / the oracle restatement are compared on the newest frame
+_add("case33_history", lambda: _case("case33"), dict(voltage_barrier_type="l1", action_scale=0.8, seed=12, history=3), (0,),
+     [("init",)] + [("step", True)] * 3 + [("reset",), ("step", True)])
 # manual starts at rows 55..58 (day 0, hour 2, interval 15 + k): the overload begins at row 60
 _add("case33_divergence", _overload_case, dict(voltage_barrier_type="l1", action_scale=0.8, seed=7), (0, 1, 2, 3),
      [("init",), ("manual", 0, 2, 15)] + [("step", False)] * 7, per_env_manual=lambda k: (0, 2, 15 + (k % 4)))

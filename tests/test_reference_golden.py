@@ -39,6 +39,7 @@ def test_fixtures_match_the_scenario_table():
         acts = S.action_stream(name, S.n_steps_of(sc), len(sc["env_ids"]), net.n_sgen, lo, hi)
         assert np.array_equal(acts, g["actions"])
         assert g["obs"].shape[:3] == (len(ops), len(sc["env_ids"]), net.n_sgen)
+        assert g["obs"].shape[3] == sc["args"].get("history", 1) * net.obs_dim or "state_space" in sc["args"]
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -70,7 +71,7 @@ def test_oracle_reproduces_the_reference_trajectories(name):
                 n_reset += 1
                 obs = np.array(obs)
             if obs is not None:
-                assert np.abs(obs - g["obs"][k_op, k]).max() < 1e-11
+                assert np.abs(obs - g["obs"][k_op, k][:, -obs.shape[1]:]).max() < 1e-11     # history > 1: the newest frame
                 assert np.abs(st - g["state"][k_op, k]).max() < 1e-9        # va_degree: 1e-11 rad x 57.3
 
 
@@ -80,7 +81,7 @@ def _reference_here():
 
 
 @pytest.mark.skipif(not _reference_here(), reason="/root/reference is not available on this machine")
-@pytest.mark.parametrize("name", ["case33_bowl", "general_line_weight", "case33_divergence", "case33_state_space"])
+@pytest.mark.parametrize("name", ["case33_bowl", "general_line_weight", "case33_divergence", "case33_state_space", "case33_history"])
 def test_reference_rerun_reproduces_the_committed_fixture(name):
     import importlib.util
     spec = importlib.util.spec_from_file_location("make_reference_golden", os.path.join(ROOT, "scripts", "make_reference_golden.py"))
@@ -185,7 +186,7 @@ def test_cuda_path_reproduces_the_reference_trajectories(name):
             n_reset += 1
             live = np.arange(len(ids))
             sel = ids
-        assert np.abs(env.obs[sel].cpu().numpy() - g["obs"][k_op, live]).max() < 1e-9
+        assert np.abs(env.obs[sel].cpu().numpy() - g["obs"][k_op, live][..., -env.obs_size:]).max() < 1e-9   # newest frame
         assert np.abs(st[sel].cpu().numpy() - g["state"][k_op, live]).max() < 1e-8
     env.close()
 
@@ -222,7 +223,7 @@ def test_drop_in_class_reproduces_the_reference_trajectories(name):
             d, h, i = g["start"][sum(1 for o in ops[:k_op] if o[0] != "step"), 0]
             assert (env._episode_start_day, env._episode_start_hour, env._episode_start_interval) == (d, h, i)
             assert env.steps == 1 and env.sum_rewards == 0
-        assert isinstance(obs, list) and len(obs) == ng and obs[0].shape == (env.get_obs_size(),)
+        assert isinstance(obs, list) and len(obs) == ng and obs[0].shape == (env.get_obs_size(),) == (g["obs"].shape[-1],)
         assert np.abs(np.array(obs) - g["obs"][k_op, 0]).max() < 1e-9
         assert state.shape == (env.get_state_size(),) and np.abs(state - g["state"][k_op, 0]).max() < 1e-8
         if "state_space" not in sc["args"]:          # default layout: [p_bus | q_bus | pv | q | vm | va_degree] (:213-230)
