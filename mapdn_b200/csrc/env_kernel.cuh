@@ -61,7 +61,11 @@ __device__ __forceinline__ double nanmax(double a, double b) { return (b > a || 
 //      synchronised with a named barrier per group; ids 3.. - 0 is __syncthreads, 1-2 the helper warp's) ----
 template <int G> __device__ __forceinline__ void grp_sync(int gidx) {
   if constexpr (G <= 32) __syncwarp();
+#ifdef MAPDN_HOST_EMU
+  else emu::bar_sync(3 + gidx, G);
+#else
   else asm volatile("bar.sync %0, %1;" ::"r"(3 + gidx), "r"(G) : "memory");
+#endif
 }
 // true iff `pred` holds on every thread of the group (includes a group barrier when G > 32)
 template <int G> __device__ __forceinline__ bool grp_all(int gidx, bool pred) {
@@ -70,6 +74,9 @@ template <int G> __device__ __forceinline__ bool grp_all(int gidx, bool pred) {
     const unsigned gmask = (G == 32) ? kFull : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
     return (ok & gmask) == gmask;
   } else {
+#ifdef MAPDN_HOST_EMU
+    return emu::bar_red_and(3 + gidx, G, pred);
+#else
     unsigned r;
     asm volatile(
         "{\n\t.reg .pred p, q;\n\t"
@@ -80,6 +87,7 @@ template <int G> __device__ __forceinline__ bool grp_all(int gidx, bool pred) {
         : "r"(static_cast<unsigned>(pred)), "r"(3 + gidx), "r"(G)
         : "memory");
     return r != 0;
+#endif
   }
 }
 // loop-exit test of the lock-step sub-warp groups: every env handled by this warp is done (G <= 32);
@@ -127,7 +135,11 @@ template <int G, int NV> __device__ __forceinline__ void grp_reduce(int gidx, in
 // "not converged" - the same outcome pandapower reaches through a singular-matrix warning.
 __device__ __forceinline__ double fast_rcp(double x) {
   double r;
+#ifdef MAPDN_HOST_EMU
+  r = static_cast<double>(static_cast<float>(1.0 / x));      // a seed of about the same quality as MUFU.RCP64H
+#else
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#endif
   const double e = fma(-x, r, 1.0);
   const double t = fma(e, e, e);
   return fma(r, t, r);
@@ -199,6 +211,12 @@ __device__ __forceinline__ double barrier_fn(int kind, double v) {
 // ---- TMA bulk copy of the hot static blob into shared memory (one thread issues) ----
 __device__ __forceinline__ void stage_hot_issue(unsigned char* smem_dst, const unsigned char* gsrc,
                                                 int bytes, uint64_t* bar) {
+#ifdef MAPDN_HOST_EMU
+  (void)bar;
+  if (threadIdx.x == 0) memcpy(smem_dst, gsrc, bytes);      // the bulk copy has landed when the barrier below releases
+  __syncthreads();
+  return;
+#endif
   const uint32_t bar_a = static_cast<uint32_t>(__cvta_generic_to_shared(bar));
   const uint32_t dst_a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
   if (threadIdx.x == 0) {
@@ -213,6 +231,10 @@ __device__ __forceinline__ void stage_hot_issue(unsigned char* smem_dst, const u
   __syncthreads();      // the barrier is initialised before anybody waits on it
 }
 __device__ __forceinline__ void stage_hot_wait(uint64_t* bar) {
+#ifdef MAPDN_HOST_EMU
+  (void)bar;
+  return;
+#endif
   const uint32_t bar_a = static_cast<uint32_t>(__cvta_generic_to_shared(bar));
   uint32_t done = 0;
   while (!done) {       // every thread waits for phase 0 of the barrier
@@ -228,11 +250,19 @@ __device__ __forceinline__ void stage_hot_wait(uint64_t* bar) {
 
 // Named barriers between the solver warps and the helper warp of a CTA (producer / consumer)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+#ifdef MAPDN_HOST_EMU
+  emu::bar_sync(id, nthreads);
+#else
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+#endif
 }
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
   __threadfence_block();
+#ifdef MAPDN_HOST_EMU
+  emu::bar_arrive(id, nthreads);
+#else
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+#endif
 }
 
 // Views of the staged static blob and of one env's shared-memory slab.
@@ -642,7 +672,11 @@ template <int G, int MODE, bool DENSE = false>
 __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_constant__ Params p) {
   static_assert(!DENSE || G == 32, "the dense fallback uses one warp per env");
   static_assert(G == 4 || G == 8 || G == 16 || G == 32 || G == 64 || G == 128, "unsupported group size");
+#ifdef MAPDN_HOST_EMU
+  unsigned char* const smem_raw = emu::dyn_smem();
+#else
   extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
   __shared__ __align__(8) uint64_t stage_bar;
   PROF_DECL
   stage_hot_issue(smem_raw, p.hot, p.hot_layout.bytes, &stage_bar);
@@ -666,6 +700,7 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
   h.ysl = hl.tables_in_blob ? reinterpret_cast<const double2*>(smem_raw + hl.ysl) : p.ysl;
   h.in_blob = hl.tables_in_blob != 0;
   h.blob = smem_raw;
+#ifndef MAPDN_HOST_EMU
   if (!hl.tables_in_blob) {      // L2 was possibly flushed: fetch the cold tables now, long before the epilogue needs them
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int k = tid * 128; k < 2 * p.n_sgen * p.obs_dim; k += nt * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.obs_off) + k));
@@ -673,6 +708,7 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
     for (int k = tid * 128; k < 32 * p.n_line; k += nt * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.line_c) + k));
     for (int k = tid * 128; k < 16 * p.npq; k += nt * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.ysl) + k));
   }
+#endif
   h.nbr_ptr = reinterpret_cast<const uint16_t*>(smem_raw + hl.nbr_ptr);
   h.nbr_idx = reinterpret_cast<const uint16_t*>(smem_raw + hl.nbr_idx);
   h.nbr_y = reinterpret_cast<const double2*>(smem_raw + hl.nbr_y);
@@ -716,7 +752,11 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
       const int n_elem = ng + 2 * nl, n_pair = (n_elem + 1) / 2, n_work = epb * n_pair;
       const int ht = threadIdx.x - n_solver_threads, T = n_helper_threads;
       int4* hs = reinterpret_cast<int4*>(smem_raw + p.helper_off);     // per env: (row lo, row hi, steps, episode)
+#ifdef MAPDN_HOST_EMU
+      emu::bar_sync(15, T);
+#else
       asm volatile("bar.sync 15, %0;" ::"r"(T) : "memory");     // helper threads only: the previous round's reads of hs are done
+#endif
       for (int e = ht; e < epb; e += T) {
         const int env_h = base + e;
         int4 v = make_int4(0, 0, 0, 0);
@@ -729,7 +769,11 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
         }
         hs[e] = v;
       }
+#ifdef MAPDN_HOST_EMU
+      emu::bar_sync(15, T);
+#else
       asm volatile("bar.sync 15, %0;" ::"r"(T) : "memory");     // helper threads only
+#endif
       named_bar_sync(1, blockDim.x);                   // the solvers have read the current rows
       constexpr int U = 4;
       for (int w0 = ht; w0 < n_work; w0 += U * T) {

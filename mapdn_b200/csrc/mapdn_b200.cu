@@ -16,6 +16,14 @@
 #include "../../include/mapdn_b200.h"
 #include "env_kernel.cuh"
 
+// kernel<<<grid, block, smem, stream>>>(args...); under MAPDN_HOST_EMU (tests/emu: the library compiled with g++ for the
+// CPU SIMT emulation, test infrastructure) the same launch runs on OS threads
+#ifdef MAPDN_HOST_EMU
+#define MAPDN_LAUNCH(kernel, grid, block, smem, stream, ...) emu::launch(kernel, grid, block, smem, stream, __VA_ARGS__)
+#else
+#define MAPDN_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+
 namespace mapdn {
 
 static thread_local std::string g_last_error;
@@ -268,7 +276,7 @@ mapdn_status launch_env_kernel(mapdn_env* e, int mode, Params& p, cudaStream_t s
   p.prof = d_prof;
 #endif
   p.helper_threads = e->helper_threads;
-  fn<<<grid, e->threads + (mode == MODE_STEP ? e->helper_threads : 0), e->smem, st>>>(p);   // MODE_STEP: + helper warps
+  MAPDN_LAUNCH(fn, grid, e->threads + (mode == MODE_STEP ? e->helper_threads : 0), e->smem, st, p);   // MODE_STEP: + helper warps
   MAPDN_CUDA(cudaGetLastError());
   e->launches++;
 #ifdef MAPDN_PROFILE
@@ -368,8 +376,8 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
     TRY(dev_upload(e, br_st, &d_st)); TRY(dev_upload(e, e->br_from, &d_f)); TRY(dev_upload(e, e->br_to, &d_t));
     TRY(dev_upload(e, gs, &d_gs)); TRY(dev_upload(e, bs, &d_bs));
     TRY(dev_alloc(e, static_cast<size_t>(8) * nbr, &d_ybr)); TRY(dev_alloc(e, static_cast<size_t>(2) * n, &d_ydiag));
-    ybus_branch_kernel<<<(nbr + 127) / 128, 128>>>(nbr, d_r, d_x, d_b, d_g, d_tap, d_sh, d_st, d_ybr);
-    ybus_diag_kernel<<<(n + 127) / 128, 128>>>(n, nbr, d_f, d_t, d_ybr, d_gs, d_bs, 1.0 / net->base_mva, d_ydiag);
+    MAPDN_LAUNCH(ybus_branch_kernel, (nbr + 127) / 128, 128, 0, 0, nbr, d_r, d_x, d_b, d_g, d_tap, d_sh, d_st, d_ybr);
+    MAPDN_LAUNCH(ybus_diag_kernel, (n + 127) / 128, 128, 0, 0, n, nbr, d_f, d_t, d_ybr, d_gs, d_bs, 1.0 / net->base_mva, d_ydiag);
     TRY_CUDA(cudaGetLastError());
     e->launches += 2;
     e->ybr.resize(static_cast<size_t>(8) * nbr);
@@ -1290,7 +1298,7 @@ mapdn_status mapdn_get_obs(mapdn_env* e, double* obs_dev, void* stream) {
   Params p = e->base;
   p.obs = obs_dev;
   const long long tot = static_cast<long long>(p.nb) * p.n_sgen * p.obs_dim;
-  get_obs_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  MAPDN_LAUNCH(get_obs_kernel, static_cast<unsigned>((tot + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream), p);
   MAPDN_CUDA(cudaGetLastError());
   e->launches++;
   return MAPDN_OK;
@@ -1302,7 +1310,7 @@ mapdn_status mapdn_get_state(mapdn_env* e, double* state_dev, void* stream) {
   Params p = e->base;
   p.state = state_dev;
   const long long tot = static_cast<long long>(p.nb) * p.state_dim;
-  get_state_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  MAPDN_LAUNCH(get_state_kernel, static_cast<unsigned>((tot + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream), p);
   MAPDN_CUDA(cudaGetLastError());
   e->launches++;
   return MAPDN_OK;
@@ -1329,21 +1337,21 @@ mapdn_status mapdn_get_field(mapdn_env* e, int32_t field, double* out_dev, void*
     case MAPDN_FIELD_Q_LOAD: src = p.cur_ql; cnt = B * p.n_load; break;
     case MAPDN_FIELD_SUM_REWARDS: src = p.sum_rewards; cnt = B; break;
     case MAPDN_FIELD_STEPS:
-      int_to_double_kernel<<<static_cast<unsigned>((B + 255) / 256), 256, 0, st>>>(B, p.steps, out_dev);
+      MAPDN_LAUNCH(int_to_double_kernel, static_cast<unsigned>((B + 255) / 256), 256, 0, st, B, p.steps, out_dev);
       MAPDN_CUDA(cudaGetLastError()); e->launches++;
       return MAPDN_OK;
     case MAPDN_FIELD_NR_ITERS:
-      int_to_double_kernel<<<static_cast<unsigned>((B + 255) / 256), 256, 0, st>>>(B, p.nr_iters, out_dev);
+      MAPDN_LAUNCH(int_to_double_kernel, static_cast<unsigned>((B + 255) / 256), 256, 0, st, B, p.nr_iters, out_dev);
       MAPDN_CUDA(cudaGetLastError()); e->launches++;
       return MAPDN_OK;
     case MAPDN_FIELD_START_ROW:
-      i64_to_double_kernel<<<static_cast<unsigned>((B + 255) / 256), 256, 0, st>>>(B, p.start_row, out_dev);
+      MAPDN_LAUNCH(i64_to_double_kernel, static_cast<unsigned>((B + 255) / 256), 256, 0, st, B, p.start_row, out_dev);
       MAPDN_CUDA(cudaGetLastError()); e->launches++;
       return MAPDN_OK;
     default: return fail(MAPDN_ERR_INVALID, "unknown field");
   }
   if (cnt == 0) return MAPDN_OK;
-  scale_copy_kernel<<<static_cast<unsigned>((cnt + 255) / 256), 256, 0, st>>>(cnt, src, scale, out_dev);
+  MAPDN_LAUNCH(scale_copy_kernel, static_cast<unsigned>((cnt + 255) / 256), 256, 0, st, cnt, src, scale, out_dev);
   MAPDN_CUDA(cudaGetLastError());
   e->launches++;
   return MAPDN_OK;

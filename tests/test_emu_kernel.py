@@ -1,0 +1,133 @@
+"""CPU tier: the kernel SOURCE (mapdn_b200/csrc/env_kernel.cuh + the C-ABI host code) compiled with g++ against
+tests/emu/cuda_runtime.h - a SIMT emulation with one OS thread per CUDA thread, counting barriers for
+__syncthreads / bar.sync / bar.arrive / bar.red, exchange arrays for __shfl / __ballot - and executed against the oracle
+and against the reference-executed fixtures. It proves the kernel's LOGIC (schedules, lock-step groups, multi-warp
+groups, helper warps, RNG, epilogue) without a GPU; the `-m gpu` tests prove the sm_100a build. The emulated library is
+test infrastructure: the product never loads it, and the device build is byte-identical with or without the
+MAPDN_HOST_EMU guards (same SASS)."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, random_tree_net
+from mapdn_b200 import cases
+from mapdn_b200.network import NetDesc, ProfileDesc
+
+sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+from emu_env import EmuEnv                                          # noqa: E402
+from oracle import ref_scenarios as S                               # noqa: E402
+from oracle.pandapower_nr import PandapowerEquivalent               # noqa: E402
+from oracle.voltage_control_ref import INFO_KEYS, VoltageControlOracle   # noqa: E402
+
+TOL = 1e-9
+
+
+@pytest.mark.parametrize("lanes", [0, 4, 16, 32, 64, 128])
+def test_emulated_solve_matches_oracle_with_identical_iteration_counts(lanes):
+    net, p, q = cases.baran_wu_nominal()
+    env = EmuEnv(net, None, dict(voltage_barrier_type="l1"), batch=5, lanes_per_env=lanes)
+    scale = np.array([1.0, 0.3, 1.6, 0.8, 2.2])[:, None]
+    rng = np.random.default_rng(lanes)
+    ps, qs = rng.uniform(0, 0.4, (5, 6)), rng.uniform(-0.3, 0.3, (5, 6))
+    out = env.solve(p[None] * scale, q[None] * scale, ps, qs)
+    pf = PandapowerEquivalent(net)
+    for k in range(5):
+        r = pf.runpp(p * scale[k, 0], q * scale[k, 0], ps[k], qs[k])
+        assert out["converged"][k] == 1 and out["iterations"][k] == r.iterations
+        assert np.abs(out["vm"][k] - r.vm_pu).max() < TOL and np.abs(out["va_deg"][k] - r.va_degree).max() < 1e-8
+        assert np.abs(out["p_bus"][k] - r.p_mw).max() < TOL and np.abs(out["pl"][k] - r.pl_mw).max() < TOL
+    env.close()
+
+
+def test_emulated_solve_general_net_and_meshed_fallback():
+    net = random_tree_net(23, 4, seed=11)                      # taps, charging, shunts, scaling, open branch, slack != 0
+    rng = np.random.default_rng(0)
+    pl, ql = rng.uniform(0, 0.3, (3, net.n_load)), rng.uniform(0, 0.1, (3, net.n_load))
+    ps, qs = rng.uniform(0.1, 0.5, (3, 4)), rng.uniform(-0.2, 0.2, (3, 4))
+    env = EmuEnv(net, None, dict(voltage_barrier_type="l1"), batch=3)
+    out = env.solve(pl, ql, ps, qs)
+    pf = PandapowerEquivalent(net)
+    for k in range(3):
+        r = pf.runpp(pl[k], ql[k], ps[k], qs[k])
+        assert out["iterations"][k] == r.iterations and np.abs(out["vm"][k] - r.vm_pu).max() < TOL
+        assert np.abs(out["q_bus"][k] - r.q_mvar).max() < TOL
+    env.close()
+    # Saadat Ex. 6.7 (meshed): the dense-LU fallback, published solution
+    z = np.array([0.02 + 0.04j, 0.01 + 0.03j, 0.0125 + 0.025j])
+    mesh = NetDesc(base_mva=100.0, n_bus=3, slack_bus=0, slack_vm=1.05, br_from=np.array([0, 0, 1]), br_to=np.array([1, 2, 2]),
+                   br_r=z.real, br_x=z.imag, load_bus=np.array([1, 2]), sgen_bus=np.array([2]), sgen_zone=np.array([1]),
+                   bus_zone=np.array([0, 1, 1]), name="saadat_6_7")
+    env = EmuEnv(mesh, None, dict(voltage_barrier_type="l1"), batch=1)
+    out = env.solve(np.array([[256.6, 138.6]]), np.array([[110.2, 45.2]]), np.zeros((1, 1)), np.zeros((1, 1)))
+    V = out["vm"][0] * np.exp(1j * np.deg2rad(out["va_deg"][0]))
+    assert np.abs(V - np.array([1.05, 0.98 - 0.06j, 1.00 - 0.05j])).max() < 1e-9
+    env.close()
+
+
+@pytest.mark.parametrize("name,barrier,batch,lanes", [("case33", "bowl", 5, 0), ("case33", "l1", 3, 4), ("case33", "bump", 9, 32),
+                                                      ("case141", "l1", 3, 0), ("case33", "l2", 2, 64),
+                                                      ("case322", "courant_beltrami", 2, 0)])
+def test_emulated_trajectory_matches_oracle(name, barrier, batch, lanes):
+    """reset (sampled start, noise, reset action) + noisy steps: helper warps, named barriers, Philox, epilogue."""
+    net, prof = cases.make_case(name), cases.make_profiles(name, n_days=4)
+    scale = cases.SCENARIOS[name]["action_scale"]
+    env = EmuEnv(net, prof, dict(voltage_barrier_type=barrier, action_scale=scale, seed=5), batch=batch, lanes_per_env=lanes,
+                 env_id_offset=100)
+    ors = [VoltageControlOracle(net, prof, env.args, env_id=100 + i) for i in range(batch)]
+    obs, st = env.reset()
+    for i, o in enumerate(ors):
+        oo, os_ = o.reset()
+        assert np.abs(np.array(oo) - obs[i]).max() < TOL and np.abs(os_ - st[i]).max() < 1e-8
+    rng = np.random.default_rng(1)
+    for t in range(3 if name != "case322" else 2):
+        a = rng.uniform(-scale, scale, (batch, net.n_sgen))
+        r, term, info = env.step(a)
+        it = env.get_field("nr_iters")[:, 0]
+        for i, o in enumerate(ors):
+            ro, to, io = o.step(a[i])
+            assert abs(ro - r[i]) < TOL and to == bool(term[i]) and it[i] == o.g.res.iterations
+            assert np.abs(np.array([io[k] for k in INFO_KEYS]) - info[i]).max() < TOL
+            assert np.abs(np.array(o.get_obs()) - env.obs[i]).max() < TOL
+    env.close()
+
+
+@pytest.mark.parametrize("name", ["case33_bowl", "general_line_weight", "case33_state_space", "case33_divergence", "case141_l1"])
+def test_emulated_kernel_reproduces_the_reference_executed_fixtures(name):
+    """The kernel source, on the CPU, against trajectories the reference's own env code produced
+    (tests/golden/ref_env_*.npz, see tests/test_reference_golden.py)."""
+    g = np.load(S.fixture_path(ROOT, name))
+    ops = [tuple(op) for op in json.loads(str(g["ops"]))]
+    sc = S.SCENARIOS[name]
+    net, prof = sc["build"]()
+    ids = sc["env_ids"]
+    B = max(ids) + 1
+    env = EmuEnv(net, prof, sc["args"], batch=B)
+    t = 0
+    for k_op, op in enumerate(ops):
+        if op[0] == "step":
+            a = np.zeros((B, net.n_sgen))
+            a[ids] = g["actions"][t]
+            r, term, info = env.step(a, add_noise=op[1])
+            live = np.nonzero(g["alive"][t])[0]
+            sel = [ids[k] for k in live]
+            if live.size:
+                assert np.abs(r[sel] - g["reward"][t, live]).max() < TOL and np.array_equal(term[sel], g["term"][t, live])
+                assert np.abs(info[sel] - g["info"][t, live]).max() < TOL
+            t += 1
+            if live.size == 0:
+                continue
+        else:
+            if op[0] == "manual":
+                start = np.zeros((B, 3), np.int32)
+                for k, e in enumerate(ids):
+                    start[e] = S.manual_of(sc, op, k)
+                env.reset(start, add_noise=False)
+            else:
+                env.reset()
+            live, sel = np.arange(len(ids)), ids
+        assert np.abs(env.obs[sel] - g["obs"][k_op, live][..., -env.dims["obs_dim"]:]).max() < TOL
+        assert np.abs(env.get_state()[sel] - g["state"][k_op, live]).max() < 1e-8
+    env.close()
