@@ -309,26 +309,46 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
   const bool extra_children = p.has_extra_children != 0;
 
   // flat start (pandapower init="auto"): |V| = vm_init, angle 0 on every PQ bus; sentinel record (slack voltage,
-  // all-zero Jacobian terms: the "no child" / "no parent" slot); trash record (idle lanes: dx = 0 for ever)
+  // all-zero Jacobian terms: the "no child" / "no parent" slot); trash record (idle lanes: dx = 0 for ever).
+  // The FIRST Newton iteration is static up to its right-hand side: at the flat start S_calc and the Jacobian are the same
+  // for every env and every step, so mapdn_create factorises J(V0) once (p.first_tab, six double2 per node: S_calc,
+  // M = D'^-1 J[i,parent] (two rows), D'^-1 (two rows), J[parent,i]) and this pass seeds the records with it: the mismatch
+  // is S_calc - S_spec, the forward sweep only eliminates the right-hand side (first_sweep below: D'^-1 from UP / DN,
+  // J[parent,i] from T), the back sweep finds M where a regular elimination would have left it (D01 / D23). pandapower
+  // computes the same factors numerically in every runpp; the iterates agree to rounding.
+  double nrm = 0.0;
   for (int i = gl; i <= npq + 1; i += G) {
     const bool sl = (i == npq);
     double2* nd = s.node(i);
     nd[A_VV] = sl ? make_double2(p.vm0, p.va0) : make_double2(p.vm_init, 0.0);
     nd[A_EF] = sl ? make_double2(p.e0, p.f0) : make_double2(p.vm_init, 0.0);
-    nd[A_UP] = make_double2(0.0, 0.0);
-    nd[A_DN] = make_double2(0.0, 0.0);
-    nd[A_T] = make_double2(0.0, 0.0);
-    nd[A_R] = make_double2(0.0, 0.0);
-    if (i >= npq) { nd[A_D01] = make_double2(1.0, 0.0); nd[A_D23] = make_double2(0.0, 1.0); }    // idle lanes eliminate an identity block: no NaN / inf arithmetic
+    if (i < npq) {
+      const double2* ft = p.first_tab + 6 * i;
+      const double2 s0 = __ldg(ft), m0 = __ldg(ft + 1), m1 = __ldg(ft + 2), di0 = __ldg(ft + 3), di1 = __ldg(ft + 4), dn = __ldg(ft + 5);
+      const double2 sp = nd[A_SP];
+      const double Fp = s0.x - sp.x, Fq = s0.y - sp.y;
+      nd[A_UP] = di0; nd[A_DN] = di1; nd[A_T] = dn;
+      nd[A_D01] = m0; nd[A_D23] = m1;
+      nd[A_R] = make_double2(-Fp, -Fq);
+      nrm = nanmax(nrm, nanmax(fabs(Fp), fabs(Fq)));
+    } else {
+      nd[A_UP] = make_double2(0.0, 0.0);
+      nd[A_DN] = make_double2(0.0, 0.0);
+      nd[A_T] = make_double2(0.0, 0.0);
+      nd[A_R] = make_double2(0.0, 0.0);
+      nd[A_D01] = make_double2(1.0, 0.0); nd[A_D23] = make_double2(0.0, 1.0);    // idle lanes eliminate an identity block: no NaN / inf arithmetic
+    }
   }
   grp_sync<G>(gidx);
 
   bool done = skip;      // this group's env converged (idle groups never hold the warp back)
+  bool first = true;     // the static first iteration (group- and warp-uniform)
   int it = 0;
   iters = 0;
   const double2 v0 = make_double2(p.e0, p.f0);
   while (true) {
     PROF(2)
+    if (!first) {
     // --- per-edge terms of (i, parent): row i / col parent and row parent / col i ---
 #pragma unroll 4
     for (int i = gl; i < npq; i += G) {
@@ -344,7 +364,7 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
     grp_sync<G>(gidx);
     PROF(3)
     // --- mismatch F = S_calc - S_spec and diagonal Jacobian blocks ---
-    double nrm = 0.0;
+    nrm = 0.0;
     auto mismatch_pass = [&](auto with_extra) {
     constexpr bool kExtra = decltype(with_extra)::value;
 #pragma unroll 4
@@ -376,6 +396,7 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
     }
     };
     if (extra_children) mismatch_pass(std::true_type{}); else mismatch_pass(std::false_type{});
+    }   // !first
     {   // ||F||inf < tol for the whole env <=> every thread of the group is below tol (NaN-safe)
       const bool ok = grp_all<G>(gidx, nrm < p.tol);
       if (!done && ok) { done = true; iters = it; }
@@ -476,7 +497,64 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
           }
         }
       };
-      if (extra_children) run_sweep(std::true_type{}); else run_sweep(std::false_type{});
+      // The static first iteration: only the right-hand side is eliminated. A step reads r, D'^-1 (two rows) and
+      // J[parent,i] from the bus's own record (seeded by the flat-start pass), subtracts the children's rhs updates
+      // (registers / shared memory, the same schedule flags as above), and leaves c = D'^-1 r in R and - if the parent
+      // fetches it from shared memory - t = J[parent,i] c in T.
+      double2 t1 = make_double2(0.0, 0.0);                 // rhs update produced by this lane's last step
+      struct Own1 { double2 r, i0, i1, d; };
+      auto load_own1 = [&](uint64_t e) {
+        const double2* nd = s.node(static_cast<int>(e & 0xFFFFu));
+        Own1 o; o.r = nd[A_R]; o.i0 = nd[A_UP]; o.i1 = nd[A_DN]; o.d = nd[A_T];
+        return o;
+      };
+      auto sweep1 = [&](auto with_extra, auto warp_only, int st0, int st1) {
+      constexpr bool kExtra = decltype(with_extra)::value;
+      constexpr bool kWarpOnly = decltype(warp_only)::value;
+      if (st0 >= st1) return;
+      uint64_t ed = h.esched[st0 * G + gl];
+      uint64_t ed_next = h.esched[min(st0 + 1, p.n_esteps - 1) * G + gl];
+      Own1 own = load_own1(ed);
+      for (int st = st0; st < st1; ++st) {
+        const uint64_t ed_next2 = h.esched[min(st + 2, p.n_esteps - 1) * G + gl];
+        const int i = static_cast<int>(ed & 0xFFFFu);
+        const int c0 = static_cast<int>((ed >> 16) & 0xFFFFu), c1 = static_cast<int>((ed >> 32) & 0xFFFFu);
+        const unsigned fl = static_cast<unsigned>(ed >> 48);
+        double2* nd = s.node(i);
+        double2 r = own.r;
+        const double2 i0 = own.i0, i1 = own.i1, d = own.d;
+        if (kWarpOnly) __syncwarp(); else grp_sync<G>(gidx);  // the previous step's rhs updates are visible
+        double2 pt = t1;
+        if (fl & kEschedLeaf) pt = make_double2(0.0, 0.0);
+        if (fl & kEschedLoad0) pt = s.node(c0)[A_T];
+        r.x -= pt.x; r.y -= pt.y;
+        const Own1 own_next = load_own1(ed_next);        // the next bus's record: nobody writes it before its own step
+        if (fl & kEschedLoad1) { const double2 qt = s.node(c1)[A_T]; r.x -= qt.x; r.y -= qt.y; }
+        if (kExtra) {
+          const int nx = static_cast<int>(fl & 0xFFu);
+#pragma unroll 1
+          for (int c = c1 + 1; c <= c1 + nx; ++c) { const double2 xt = s.node(c)[A_T]; r.x -= xt.x; r.y -= xt.y; }
+        }
+        const double c0v = i0.x * r.x + i0.y * r.y, c1v = i1.x * r.x + i1.y * r.y;          // D'^-1 r
+        t1 = make_double2(d.x * c0v + d.y * c1v, d.x * c1v - d.y * c0v);                    // J[parent,i] D'^-1 r
+        if (fl & kEschedStore) nd[A_T] = t1;
+        if (!(fl & kEschedIdle)) nd[A_R] = make_double2(c0v, c1v);
+        ed = ed_next; ed_next = ed_next2; own = own_next;
+      }
+      };
+      auto run_sweep1 = [&](auto with_extra) {
+        if constexpr (G <= 32) {
+          sweep1(with_extra, std::false_type{}, 0, p.n_esteps);
+        } else {
+          sweep1(with_extra, std::false_type{}, 0, p.n_wide_e);
+          if (p.n_wide_e < p.n_esteps) {
+            if (p.n_wide_e > 0) grp_sync<G>(gidx);
+            if ((gl >> 5) == 0) sweep1(with_extra, std::true_type{}, p.n_wide_e, p.n_esteps);
+          }
+        }
+      };
+      if (first) { if (extra_children) run_sweep1(std::true_type{}); else run_sweep1(std::false_type{}); }
+      else if (extra_children) run_sweep(std::true_type{}); else run_sweep(std::false_type{});
       PROF_COUNT(15)
       grp_sync<G>(gidx);                                 // the last step's results are visible to the back sweep
     }
@@ -540,6 +618,7 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
       }
     }
     grp_sync<G>(gidx);
+    first = false;
     PROF(6)
   }
   return done;

@@ -92,6 +92,8 @@ struct Params {
   const uint16_t* line_nodes;                                 // [2*n_line] from / to node of every line (npq = slack)
   const double* line_c;                                       // [4*n_line] loss coefficients (see mapdn_b200.cu)
   const int* sgen_node;                                       // [n_sgen] node of each sgen's bus (slack -> npq)
+  // the static first Newton iteration (flat start): per node S_calc, M rows 0/1, D'^-1 rows 0/1, J[parent,i]
+  const double2* first_tab;                                   // [6 * npq]
   const double* sh_g; const double* sh_b;                     // [npq + 1] bus shunt GS / BS (MW / MVAr at 1 p.u.) by node
   const unsigned* obs_src; const int* obs_xptr; const int* obs_xidx;   // cold obs program of get_obs_kernel
   const unsigned* state_src;                                  // state program: kind | bus / sgen index

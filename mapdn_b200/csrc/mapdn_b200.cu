@@ -1088,6 +1088,60 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
   P.ysl_g0 = e->ydiag[2 * slack]; P.ysl_b0 = e->ydiag[2 * slack + 1];
   P.tol = (cfg->tol > 0) ? cfg->tol : 1e-8;
   P.max_iter = (cfg->max_iter > 0) ? cfg->max_iter : 10;
+  {
+    // The first Newton iteration starts from the flat start, where S_calc and the Jacobian depend on the network only:
+    // factorise J(V0) once, leaf -> root on the elimination forest, with the formulas of the kernel's edge / mismatch pass
+    // and elimination step (env_kernel.cuh: nr_solve). Per node six double2: S_calc = (P, Q); M = D'^-1 J[i,parent] rows
+    // 0 / 1 (what the back sweep multiplies dx_parent with); D'^-1 rows 0 / 1; J[parent,i] = (a, b).
+    std::vector<double> ft(static_cast<size_t>(12) * std::max(1, npq), 0.0);
+    if (!meshed) {
+      const double* yup = reinterpret_cast<const double*>(hot.data() + hl.yup);
+      const double* ydn = reinterpret_cast<const double*>(hot.data() + hl.ydn);
+      const double* yii = reinterpret_cast<const double*>(hot.data() + hl.yii);
+      std::vector<std::vector<int>> kids(npq);
+      std::vector<int> topo;                               // parents before children
+      for (int i = 0; i < npq; ++i) if (parent[i] >= 0) kids[parent[i]].push_back(i); else topo.push_back(i);
+      for (size_t qh = 0; qh < topo.size(); ++qh) for (int c : kids[topo[qh]]) topo.push_back(c);
+      const double vi_x = P.vm_init, vi_y = 0.0;             // every PQ bus
+      std::vector<double> upx(npq), upy(npq), dnx(npq), dny(npq), d01x(npq), d01y(npq), d23x(npq), d23y(npq);
+      for (int i = 0; i < npq; ++i) {                      // edge terms of (i, parent); roots: Y = 0
+        const double vp_x = P.vm_init, vp_y = 0.0;
+        const double cc = vi_x * vp_x + vi_y * vp_y, ss = vi_y * vp_x - vi_x * vp_y;
+        upx[i] = yup[2 * i] * ss - yup[2 * i + 1] * cc; upy[i] = yup[2 * i] * cc + yup[2 * i + 1] * ss;
+        dnx[i] = -ydn[2 * i] * ss - ydn[2 * i + 1] * cc; dny[i] = ydn[2 * i] * cc - ydn[2 * i + 1] * ss;
+      }
+      for (int i = 0; i < npq; ++i) {                      // S_calc and the diagonal blocks
+        const double cs0 = vi_x * P.e0 + vi_y * P.f0, sn0 = vi_y * P.e0 - vi_x * P.f0;
+        double sa = ysl_cold[2 * i] * sn0 - ysl_cold[2 * i + 1] * cs0 + upx[i];
+        double sb = ysl_cold[2 * i] * cs0 + ysl_cold[2 * i + 1] * sn0 + upy[i];
+        for (int c : kids[i]) { sa += dnx[c]; sb += dny[c]; }
+        const double vv = vi_x * vi_x + vi_y * vi_y;
+        const double gv = yii[2 * i] * vv, bv = yii[2 * i + 1] * vv;
+        const double Pc = gv + sb, Qc = sa - bv;
+        ft[12 * i + 0] = Pc; ft[12 * i + 1] = Qc;
+        d01x[i] = -Qc - bv; d01y[i] = Pc + gv; d23x[i] = Pc - gv; d23y[i] = Qc - bv;
+      }
+      for (size_t k = topo.size(); k-- > 0;) {              // children before parents
+        const int i = topo[k];
+        const double idet = 1.0 / (d01x[i] * d23y[i] - d01y[i] * d23x[i]);
+        const double ux = upx[i], uy = upy[i], dx = dnx[i], dy = dny[i];
+        const double ma00 = d23y[i] * ux + d01y[i] * uy, ma01 = d23y[i] * uy - d01y[i] * ux;      // adj(D') J[i,parent]
+        const double ma10 = -d23x[i] * ux - d01x[i] * uy, ma11 = d01x[i] * ux - d23x[i] * uy;
+        ft[12 * i + 2] = ma00 * idet; ft[12 * i + 3] = ma01 * idet; ft[12 * i + 4] = ma10 * idet; ft[12 * i + 5] = ma11 * idet;
+        ft[12 * i + 6] = d23y[i] * idet; ft[12 * i + 7] = -d01y[i] * idet;                         // D'^-1
+        ft[12 * i + 8] = -d23x[i] * idet; ft[12 * i + 9] = d01x[i] * idet;
+        ft[12 * i + 10] = dx; ft[12 * i + 11] = dy;
+        if (parent[i] >= 0) {                               // Schur update of the parent: J[parent,i] D'^-1 J[i,parent]
+          const int pa = parent[i];
+          d01x[pa] -= (dx * ma00 + dy * ma10) * idet; d01y[pa] -= (dx * ma01 + dy * ma11) * idet;
+          d23x[pa] -= (dx * ma10 - dy * ma00) * idet; d23y[pa] -= (dx * ma11 - dy * ma01) * idet;
+        }
+      }
+    }
+    const double* d_ft = nullptr;
+    TRY(dev_upload(e, ft, &d_ft));
+    P.first_tab = reinterpret_cast<const double2*>(d_ft);
+  }
   P.barrier = cfg->barrier; P.voltage_weight = cfg->voltage_weight; P.q_weight = cfg->q_weight;
   P.line_weight = cfg->line_weight; P.use_line_weight = cfg->use_line_weight;
   P.v_upper = cfg->v_upper; P.v_lower = cfg->v_lower; P.episode_limit = cfg->episode_limit;

@@ -131,3 +131,63 @@ def test_emulated_kernel_reproduces_the_reference_executed_fixtures(name):
         assert np.abs(env.obs[sel] - g["obs"][k_op, live][..., -env.dims["obs_dim"]:]).max() < TOL
         assert np.abs(env.get_state()[sel] - g["state"][k_op, live]).max() < 1e-8
     env.close()
+
+
+def _check_solve(net, lanes_list, B, rng, pl_hi, pv_hi):
+    pf = PandapowerEquivalent(net)
+    pl = rng.uniform(0.0, pl_hi, (B, net.n_load)); ql = 0.35 * pl
+    pv = rng.uniform(0.0, pv_hi, (B, net.n_sgen)); q = rng.uniform(-0.3 * pv_hi, 0.3 * pv_hi, (B, net.n_sgen))
+    for lanes in lanes_list:
+        env = EmuEnv(net, None, dict(voltage_barrier_type="l1"), batch=1, lanes_per_env=lanes)
+        out = env.solve(pl, ql, pv, q)
+        for e in range(B):
+            r = pf.runpp(pl[e], ql[e], pv[e], q[e])
+            assert r.converged and out["converged"][e] == 1 and out["iterations"][e] == r.iterations
+            assert np.abs(out["vm"][e] - r.vm_pu).max() < TOL and np.abs(out["va_deg"][e] - r.va_degree).max() < 1e-8
+            assert np.abs(out["p_bus"][e] - r.p_mw).max() < 1e-8 and np.abs(out["pl"][e] - r.pl_mw).max() < TOL
+        env.close()
+
+
+def test_emulated_degenerate_topologies_and_hubs():
+    """2-bus net, a star (forest of single-bus trees: no back sweep), a chain of 40 buses, and a net with a six-child hub
+    plus a second hub (the > 2 children path of the sweeps), several lane counts - the same cases as the GPU tier."""
+    rng = np.random.default_rng(5)
+    two = NetDesc(base_mva=1.0, n_bus=2, slack_bus=1, slack_vm=1.01, br_from=[0], br_to=[1], br_r=[0.01], br_x=[0.02],
+                  load_bus=[0], sgen_bus=[0], sgen_zone=[1], bus_zone=[1, 0])
+    n = 9
+    star = NetDesc(base_mva=1.0, n_bus=n, slack_bus=4, slack_vm=1.0, br_from=[4] * (n - 1), br_to=[b for b in range(n) if b != 4],
+                   br_r=rng.uniform(0.005, 0.02, n - 1), br_x=rng.uniform(0.005, 0.02, n - 1), load_bus=np.arange(n),
+                   sgen_bus=[0, 8], sgen_zone=[1, 2], bus_zone=[1, 1, 1, 1, 0, 2, 2, 2, 2])
+    n = 40
+    chain = NetDesc(base_mva=1.0, n_bus=n, slack_bus=0, slack_vm=1.0, br_from=np.arange(n - 1), br_to=np.arange(1, n),
+                    br_r=rng.uniform(0.001, 0.004, n - 1), br_x=rng.uniform(0.001, 0.004, n - 1), load_bus=np.arange(1, n),
+                    sgen_bus=[n - 1, n // 2], sgen_zone=[1, 1], bus_zone=[0] + [1] * (n - 1))
+    for net in (two, star, chain):
+        _check_solve(net, (0, 4, 32), 4, rng, 0.05, 0.2)
+    f, t = [0], [1]
+    nxt = 2
+    for k in range(6):
+        f += [1, nxt, nxt + 1]; t += [nxt, nxt + 1, nxt + 2]; nxt += 3
+    for k in range(4):
+        f.append(4); t.append(nxt); nxt += 1
+    n = nxt
+    hub = NetDesc(base_mva=1.0, n_bus=n, slack_bus=0, slack_vm=1.0, br_from=f, br_to=t, br_r=rng.uniform(0.002, 0.01, n - 1),
+                  br_x=rng.uniform(0.002, 0.01, n - 1), load_bus=np.arange(1, n), sgen_bus=[3, 10, n - 1], sgen_zone=[1, 1, 1],
+                  bus_zone=[0] + [1] * (n - 1))
+    _check_solve(hub, (4, 8, 32, 64), 5, rng, 0.06, 0.3)
+
+
+def test_emulated_divergence_flag_and_ragged_batches():
+    net, p, q = cases.baran_wu_nominal()
+    env = EmuEnv(net, None, dict(voltage_barrier_type="l1"), batch=1)
+    out = env.solve(np.stack([p, p * 40, p]), np.stack([q, q * 40, q]), np.zeros((3, 6)), np.zeros((3, 6)))
+    assert out["converged"].tolist() == [1, 0, 1] and out["iterations"][1] == 10
+    assert np.abs(out["vm"][0] - out["vm"][2]).max() == 0.0
+    pf = PandapowerEquivalent(net)
+    for nb in (1, 2, 3, 17, 33):
+        inp = cases.synthetic_inputs("case33", nb, seed=nb)
+        qs = inp["action"] * np.sqrt(inp["s_max"] ** 2 - inp["p_pv"] ** 2)
+        out = env.solve(inp["p_load"], inp["q_load"], inp["p_pv"], qs)
+        for e in range(nb):
+            assert np.abs(out["vm"][e] - pf.runpp(inp["p_load"][e], inp["q_load"][e], inp["p_pv"][e], qs[e]).vm_pu).max() < TOL
+    env.close()
