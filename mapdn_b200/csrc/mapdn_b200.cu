@@ -1098,12 +1098,20 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
       const double* yup = reinterpret_cast<const double*>(hot.data() + hl.yup);
       const double* ydn = reinterpret_cast<const double*>(hot.data() + hl.ydn);
       const double* yii = reinterpret_cast<const double*>(hot.data() + hl.yii);
+      // children in a labelling-independent order (first child, second child, then the contiguous extras): the node
+      // relabelling of section 2b must not change a single bit of the results
       std::vector<std::vector<int>> kids(npq);
+      for (int i = 0; i < npq; ++i) {
+        if (kid0[i] != npq) kids[i].push_back(kid0[i]);
+        if (kid1[i] != npq) kids[i].push_back(kid1[i]);
+        for (int c = 2; c < nchild[i]; ++c) kids[i].push_back(kid1[i] + c - 1);      // extras follow child 1 contiguously
+      }
       std::vector<int> topo;                               // parents before children
-      for (int i = 0; i < npq; ++i) if (parent[i] >= 0) kids[parent[i]].push_back(i); else topo.push_back(i);
+      for (int i = 0; i < npq; ++i) if (parent[i] < 0) topo.push_back(i);
       for (size_t qh = 0; qh < topo.size(); ++qh) for (int c : kids[topo[qh]]) topo.push_back(c);
       const double vi_x = P.vm_init, vi_y = 0.0;             // every PQ bus
       std::vector<double> upx(npq), upy(npq), dnx(npq), dny(npq), d01x(npq), d01y(npq), d23x(npq), d23y(npq);
+      std::vector<double> s00(npq, 0.0), s01(npq, 0.0), s10(npq, 0.0), s11(npq, 0.0);     // Schur update a bus hands to its parent
       for (int i = 0; i < npq; ++i) {                      // edge terms of (i, parent); roots: Y = 0
         const double vp_x = P.vm_init, vp_y = 0.0;
         const double cc = vi_x * vp_x + vi_y * vp_y, ss = vi_y * vp_x - vi_x * vp_y;
@@ -1123,6 +1131,7 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
       }
       for (size_t k = topo.size(); k-- > 0;) {              // children before parents
         const int i = topo[k];
+        for (int c : kids[i]) { d01x[i] -= s00[c]; d01y[i] -= s01[c]; d23x[i] -= s10[c]; d23y[i] -= s11[c]; }
         const double idet = 1.0 / (d01x[i] * d23y[i] - d01y[i] * d23x[i]);
         const double ux = upx[i], uy = upy[i], dx = dnx[i], dy = dny[i];
         const double ma00 = d23y[i] * ux + d01y[i] * uy, ma01 = d23y[i] * uy - d01y[i] * ux;      // adj(D') J[i,parent]
@@ -1131,11 +1140,8 @@ mapdn_status mapdn_create(const mapdn_net_desc* net, const mapdn_profile_desc* p
         ft[12 * i + 6] = d23y[i] * idet; ft[12 * i + 7] = -d01y[i] * idet;                         // D'^-1
         ft[12 * i + 8] = -d23x[i] * idet; ft[12 * i + 9] = d01x[i] * idet;
         ft[12 * i + 10] = dx; ft[12 * i + 11] = dy;
-        if (parent[i] >= 0) {                               // Schur update of the parent: J[parent,i] D'^-1 J[i,parent]
-          const int pa = parent[i];
-          d01x[pa] -= (dx * ma00 + dy * ma10) * idet; d01y[pa] -= (dx * ma01 + dy * ma11) * idet;
-          d23x[pa] -= (dx * ma10 - dy * ma00) * idet; d23y[pa] -= (dx * ma11 - dy * ma01) * idet;
-        }
+        s00[i] = (dx * ma00 + dy * ma10) * idet; s01[i] = (dx * ma01 + dy * ma11) * idet;         // J[parent,i] D'^-1 J[i,parent]
+        s10[i] = (dx * ma10 - dy * ma00) * idet; s11[i] = (dx * ma11 - dy * ma01) * idet;
       }
     }
     const double* d_ft = nullptr;

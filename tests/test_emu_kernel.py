@@ -191,3 +191,23 @@ def test_emulated_divergence_flag_and_ragged_batches():
         for e in range(nb):
             assert np.abs(out["vm"][e] - pf.runpp(inp["p_load"][e], inp["q_load"][e], inp["p_pv"][e], qs[e]).vm_pu).max() < TOL
     env.close()
+
+
+def test_emulated_node_relabelling_changes_addresses_not_results(monkeypatch):
+    """The bank-conflict-aware node ids only move records inside shared memory; the static first-iteration factors are
+    accumulated in a labelling-independent order: bit-identical results with and without the relabelling."""
+    net, prof = cases.make_case("case33"), cases.make_profiles("case33", n_days=4)
+    args = dict(seed=6, voltage_barrier_type="bowl")
+    monkeypatch.setenv("MAPDN_NO_RELABEL", "1")
+    e0 = EmuEnv(net, prof, args, batch=6)
+    monkeypatch.delenv("MAPDN_NO_RELABEL")
+    e1 = EmuEnv(net, prof, args, batch=6)
+    o0, s0 = e0.reset(); o1, s1 = e1.reset()
+    assert np.array_equal(o0, o1) and np.array_equal(s0, s1)
+    rng = np.random.default_rng(0)
+    for _ in range(3):
+        a = rng.uniform(-0.8, 0.8, (6, 6))
+        r0, t0, i0 = e0.step(a); r1, t1, i1 = e1.step(a)
+        assert np.array_equal(r0, r1) and np.array_equal(i0, i1) and np.array_equal(e0.obs, e1.obs)
+        assert np.array_equal(e0.get_field("vm"), e1.get_field("vm"))
+    e0.close(); e1.close()
