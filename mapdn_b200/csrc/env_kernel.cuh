@@ -317,26 +317,36 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
   // J[parent,i] from T), the back sweep finds M where a regular elimination would have left it (D01 / D23). pandapower
   // computes the same factors numerically in every runpp; the iterates agree to rounding.
   double nrm = 0.0;
-  for (int i = gl; i <= npq + 1; i += G) {
-    const bool sl = (i == npq);
-    double2* nd = s.node(i);
-    nd[A_VV] = sl ? make_double2(p.vm0, p.va0) : make_double2(p.vm_init, 0.0);
-    nd[A_EF] = sl ? make_double2(p.e0, p.f0) : make_double2(p.vm_init, 0.0);
-    if (i < npq) {
+  {
+    // the six double2 of the next bus are requested one pass iteration ahead (read-only path; the table sits in L2 / L1)
+    struct First { double2 s0, m0, m1, i0, i1, dn; };
+    auto load_first = [&](int i) {
       const double2* ft = p.first_tab + 6 * i;
-      const double2 s0 = __ldg(ft), m0 = __ldg(ft + 1), m1 = __ldg(ft + 2), di0 = __ldg(ft + 3), di1 = __ldg(ft + 4), dn = __ldg(ft + 5);
-      const double2 sp = nd[A_SP];
-      const double Fp = s0.x - sp.x, Fq = s0.y - sp.y;
-      nd[A_UP] = di0; nd[A_DN] = di1; nd[A_T] = dn;
-      nd[A_D01] = m0; nd[A_D23] = m1;
-      nd[A_R] = make_double2(-Fp, -Fq);
-      nrm = nanmax(nrm, nanmax(fabs(Fp), fabs(Fq)));
-    } else {
-      nd[A_UP] = make_double2(0.0, 0.0);
-      nd[A_DN] = make_double2(0.0, 0.0);
-      nd[A_T] = make_double2(0.0, 0.0);
-      nd[A_R] = make_double2(0.0, 0.0);
-      nd[A_D01] = make_double2(1.0, 0.0); nd[A_D23] = make_double2(0.0, 1.0);    // idle lanes eliminate an identity block: no NaN / inf arithmetic
+      First f; f.s0 = __ldg(ft); f.m0 = __ldg(ft + 1); f.m1 = __ldg(ft + 2); f.i0 = __ldg(ft + 3); f.i1 = __ldg(ft + 4); f.dn = __ldg(ft + 5);
+      return f;
+    };
+    First nxt = load_first(min(gl, npq - 1));
+    for (int i = gl; i <= npq + 1; i += G) {
+      const First cur = nxt;
+      nxt = load_first(min(i + G, npq - 1));               // clamped: the last lanes re-read bus npq - 1 (unused)
+      const bool sl = (i == npq);
+      double2* nd = s.node(i);
+      nd[A_VV] = sl ? make_double2(p.vm0, p.va0) : make_double2(p.vm_init, 0.0);
+      nd[A_EF] = sl ? make_double2(p.e0, p.f0) : make_double2(p.vm_init, 0.0);
+      if (i < npq) {
+        const double2 sp = nd[A_SP];
+        const double Fp = cur.s0.x - sp.x, Fq = cur.s0.y - sp.y;
+        nd[A_UP] = cur.i0; nd[A_DN] = cur.i1; nd[A_T] = cur.dn;
+        nd[A_D01] = cur.m0; nd[A_D23] = cur.m1;
+        nd[A_R] = make_double2(-Fp, -Fq);
+        nrm = nanmax(nrm, nanmax(fabs(Fp), fabs(Fq)));
+      } else {
+        nd[A_UP] = make_double2(0.0, 0.0);
+        nd[A_DN] = make_double2(0.0, 0.0);
+        nd[A_T] = make_double2(0.0, 0.0);
+        nd[A_R] = make_double2(0.0, 0.0);
+        nd[A_D01] = make_double2(1.0, 0.0); nd[A_D23] = make_double2(0.0, 1.0);    // idle lanes eliminate an identity block: no NaN / inf arithmetic
+      }
     }
   }
   grp_sync<G>(gidx);
@@ -786,6 +796,14 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
     for (int k = tid * 128; k < 4 * p.n_line; k += nt * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.line_nodes) + k));
     for (int k = tid * 128; k < 32 * p.n_line; k += nt * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.line_c) + k));
     for (int k = tid * 128; k < 16 * p.npq; k += nt * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.ysl) + k));
+  }
+#endif
+#ifndef MAPDN_HOST_EMU
+  if (!DENSE) {   // the factors of the static first Newton iteration (96 B per bus, read by every solve's flat-start pass): after an
+                  // L2 flush their first touch would be a chain of DRAM round trips in front of the first sweep - fetch them
+                  // into L2 now, behind the prologue
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int k = tid * 128; k < 96 * p.npq; k += nt * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.first_tab) + k));
   }
 #endif
   h.nbr_ptr = reinterpret_cast<const uint16_t*>(smem_raw + hl.nbr_ptr);
