@@ -50,6 +50,12 @@ def lib():
         L.mapdn_get_field.argtypes = [vp, C.c_int32, vp, vp]
         L.mapdn_solve.argtypes = [vp, C.c_int32] + [vp] * 11 + [vp]
         L.mapdn_droop.argtypes = [vp, C.c_int32] + [vp] * 5 + [C.c_double, C.c_double, C.c_int32] + [vp] * 5
+        L.mapdn_step_host.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, vp]
+        L.mapdn_step_host_f32obs.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, vp]
+        L.mapdn_step_host_pinned.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]
+        L.mapdn_step_host_compact.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp]
+        L.mapdn_obs_compact_layout.argtypes = [vp, vp, vp, vp]
+        L.mapdn_wait.argtypes = [vp, vp]
         _L = L
     return _L
 
@@ -135,3 +141,37 @@ class EmuEnv:
         out = np.zeros((self.batch, width))
         self._chk(lib().mapdn_get_field(self._h, _capi.FIELDS[name], _ptr(out), None))
         return out
+
+    # ---- host-buffer entry points (under the emulation every buffer is "pinned host memory") ----
+    def compact_layout(self):
+        n = self.dims["n_agents"]
+        off, ln, row = (C.c_int32 * n)(), (C.c_int32 * n)(), C.c_int32(0)
+        self._chk(lib().mapdn_obs_compact_layout(self._h, off, ln, C.byref(row)))
+        return [(int(off[a]), int(ln[a])) for a in range(n)], int(row.value)
+
+    def step_host(self, actions, add_noise=True, f32=False, path="pinned", direct=False):
+        """path: "pinned" (zero-copy, padding skipped), "staged" (H2D + 4 x D2H), "compact" (rows without padding)."""
+        a = np.ascontiguousarray(actions, np.float64)
+        d, B = self.dims, self.batch
+        dt = np.float32 if f32 else np.float64
+        if path == "compact":
+            obs = np.zeros((B, self.compact_layout()[1]), dt)
+            self._chk(lib().mapdn_step_host_compact(self._h, _ptr(a), int(add_noise), _ptr(self.reward), _ptr(self.term),
+                                                    _ptr(self.info), _ptr(obs), int(f32), int(direct), 1, None))
+        elif path == "pinned":
+            obs = np.zeros((B, d["n_agents"], d["obs_dim"]), dt)      # the padding is never written: it must start as zeros
+            self._chk(lib().mapdn_step_host_pinned(self._h, _ptr(a), int(add_noise), _ptr(self.reward), _ptr(self.term),
+                                                   _ptr(self.info), _ptr(obs), int(f32), 1, 1, None))
+        else:
+            obs = np.full((B, d["n_agents"], d["obs_dim"]), np.nan, dt)
+            fn = lib().mapdn_step_host_f32obs if f32 else lib().mapdn_step_host
+            self._chk(fn(self._h, _ptr(a), int(add_noise), _ptr(self.reward), _ptr(self.term), _ptr(self.info), _ptr(obs), None))
+        return self.reward.copy(), self.term.copy(), self.info.copy(), obs
+
+    def droop(self, p_load, q_load, p_pv, s_rated, gain=0.1, tol=1e-4, max_ite=100):
+        B, d = p_pv.shape[0], self.dims
+        ins = [np.ascontiguousarray(x, np.float64) for x in (p_load, q_load, p_pv, s_rated, s_rated)]
+        vm, q, loss, it = np.zeros((B, d["n_bus"])), np.zeros((B, d["n_sgen"])), np.zeros(B), np.zeros(B, np.int32)
+        self._chk(lib().mapdn_droop(self._h, B, *[_ptr(x) for x in ins], float(gain), float(tol), int(max_ite), _ptr(vm), _ptr(q),
+                                    _ptr(loss), _ptr(it), None))
+        return dict(vm=vm, q=q, loss=loss, iterations=it)

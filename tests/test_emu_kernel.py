@@ -211,3 +211,81 @@ def test_emulated_node_relabelling_changes_addresses_not_results(monkeypatch):
         assert np.array_equal(r0, r1) and np.array_equal(i0, i1) and np.array_equal(e0.obs, e1.obs)
         assert np.array_equal(e0.get_field("vm"), e1.get_field("vm"))
     e0.close(); e1.close()
+
+
+def _oracle_droop(net, pl, ql, pv, s_rated, max_ite=100, gain=0.1):
+    """Literal restatement of reference traditional_control/pf_droop_matpower_all.m:121-152,196-231 (one instant)."""
+    pf = PandapowerEquivalent(net)
+
+    def droop(p, s, v, qmm):
+        q_max = min(np.sqrt(s * s - p * p), qmm)
+        if v <= 0.95: return q_max
+        if v > 1.05: return -q_max
+        if 1.0 <= v <= 1.0: return 0.0
+        if v < 1.0: return (q_max - 0) / (0.95 - 1.0) * (v - 1.0)
+        return (0 - q_max) / (1.0 - 1.05) * (1.0 - v)
+    q_last = np.zeros(net.n_sgen); v_last = 100 * np.ones(net.n_sgen)
+    for i in range(max_ite):
+        res = pf.runpp(pl, ql, pv, q_last)
+        v = res.vm_pu[net.sgen_bus]
+        if np.linalg.norm(v_last - v) < 1e-4:
+            break
+        v_last = v
+        q_new = np.array([droop(pv[j], s_rated[j], v[j], s_rated[j]) for j in range(net.n_sgen)])
+        q_last = (1 - gain) * q_last + gain * q_new
+    return res.vm_pu, q_last, res.pl_mw.sum(), i + 1
+
+
+def test_emulated_droop_baseline_matches_the_script():
+    """MODE_DROOP (one launch: the relaxed loop of <= 100 power flows, per-env stopping rule) on the tree solver and on the
+    dense fallback of a meshed net."""
+    net = cases.case33()
+    inp = cases.synthetic_inputs("case33", 5, seed=4)
+    env = EmuEnv(net, None, None, batch=1)
+    out = env.droop(inp["p_load"], inp["q_load"], inp["p_pv"], inp["s_max"])
+    for e in range(5):
+        vm, q, loss, it = _oracle_droop(net, inp["p_load"][e], inp["q_load"][e], inp["p_pv"][e], inp["s_max"])
+        assert out["iterations"][e] == it and np.abs(out["vm"][e] - vm).max() < 1e-8
+        assert np.abs(out["q"][e] - q).max() < 1e-8 and abs(out["loss"][e] - loss) < 1e-8
+    env.close()
+    z = np.array([0.02 + 0.04j, 0.01 + 0.03j, 0.0125 + 0.025j, 0.015 + 0.03j])
+    mesh = NetDesc(base_mva=100.0, n_bus=4, slack_bus=0, slack_vm=1.03, br_from=np.array([0, 0, 1, 2]), br_to=np.array([1, 2, 2, 3]),
+                   br_r=z.real, br_x=z.imag, load_bus=np.array([1, 2, 3]), sgen_bus=np.array([2, 3]), sgen_zone=np.array([1, 1]),
+                   bus_zone=np.array([0, 1, 1, 1]), name="mesh4")
+    env = EmuEnv(mesh, None, None, batch=1)
+    rng = np.random.default_rng(2)
+    pl = rng.uniform(80, 260, (4, 3)); ql = pl * rng.uniform(0.2, 0.5, (4, 3)); pv = rng.uniform(0, 60, (4, 2))
+    out = env.droop(pl, ql, pv, np.array([80.0, 80.0]))
+    for e in range(4):
+        vm, q, loss, it = _oracle_droop(mesh, pl[e], ql[e], pv[e], np.array([80.0, 80.0]))
+        assert out["iterations"][e] == it and it > 2 and np.abs(out["vm"][e] - vm).max() < 1e-8 and np.abs(out["q"][e] - q).max() < 1e-7
+    env.close()
+
+
+@pytest.mark.parametrize("scenario,batch", [("case33", 6), ("case141", 2)])
+def test_emulated_host_paths_deliver_the_same_transition(scenario, batch):
+    """mapdn_step (device buffers) == mapdn_step_host (staged copies) == mapdn_step_host_pinned (zero-copy, padding not
+    rewritten) == mapdn_step_host_compact (rows without the padding, copied or written directly), fp64 and fp32."""
+    net, prof = cases.make_case(scenario), cases.make_profiles(scenario, n_days=3)
+    envs = [EmuEnv(net, prof, dict(seed=11), batch=batch) for _ in range(6)]
+    for e in envs:
+        e.reset()
+    slices, row = envs[0].compact_layout()
+    assert len(slices) == net.n_sgen and row % 4 == 0 and sum(n for _, n in slices) <= row < sum(n for _, n in slices) + 4
+    rng = np.random.default_rng(5)
+    for t in range(2):
+        act = rng.uniform(-0.6, 0.6, (batch, net.n_sgen))
+        r, tm, info = envs[0].step(act)
+        ref = envs[0].obs
+        outs = [envs[1].step_host(act, path="staged"), envs[2].step_host(act, path="pinned"),
+                envs[3].step_host(act, path="compact", direct=bool(t & 1)), envs[4].step_host(act, path="compact", f32=True, direct=not (t & 1)),
+                envs[5].step_host(act, path="pinned", f32=True)]
+        for k, (r2, t2, i2, o2) in enumerate(outs):
+            assert np.array_equal(r, r2) and np.array_equal(tm, t2) and np.array_equal(info, i2), k
+        assert np.array_equal(outs[0][3], ref) and np.array_equal(outs[1][3], ref) and np.array_equal(outs[4][3], ref.astype(np.float32))
+        for o, dt in ((outs[2][3], np.float64), (outs[3][3], np.float32)):
+            for a, (off, n) in enumerate(slices):
+                assert np.array_equal(o[:, off:off + n], ref[:, a, :n].astype(dt)) and not np.any(ref[:, a, n:])
+            assert not np.any(o[:, sum(n for _, n in slices):])
+    for e in envs:
+        e.close()
