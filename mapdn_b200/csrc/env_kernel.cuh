@@ -940,12 +940,14 @@ __global__ void __launch_bounds__(G > 32 ? 640 : 384) env_kernel(const __grid_co
     RngKey key{k0, k1, static_cast<uint32_t>(p.env_id_offset + env), 0u};
     long long start = 0;
     int steps_old = 0;
-    if (MODE == MODE_STEP) {
+    // (groups beyond the batch work on a clamped env id without storing anything: they must not read the scalars that the
+    // env's real group rewrites at the end of its step / reset - a benign race, but a race)
+    if (MODE == MODE_STEP && valid) {
       key.c3base = p.episode[env] * 8u;
       start = p.start_row[env];
       steps_old = p.steps[env];
     }
-    if (MODE == MODE_RESET) key.c3base = (p.episode[env] + 1u) * 8u;
+    if (MODE == MODE_RESET && valid) key.c3base = (p.episode[env] + 1u) * 8u;
 
     bool conv = false;
     int iters = 0;
