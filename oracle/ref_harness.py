@@ -31,7 +31,6 @@ Nothing here is imported by the product; only ``scripts/make_reference_golden.py
 from __future__ import annotations
 
 import contextlib
-import copy
 import io
 import os
 import pickle

@@ -100,3 +100,19 @@ def test_create_validates_arguments_without_touching_the_gpu(built_lib):
     # null handles are refused, not dereferenced
     assert L.mapdn_step(None, None, 0, None, None, None, None, None) == 1
     assert L.mapdn_destroy(None) == 0
+
+
+def test_product_library_is_the_device_build_not_the_cpu_emulation(built_lib):
+    """The shipped library is the nvcc build: it carries sm_100a device code and none of the emulation's symbols; the
+    product's loader and build script know nothing of tests/emu (the CPU SIMT emulation is test infrastructure)."""
+    import subprocess
+    from mapdn_b200 import build
+    assert "-DMAPDN_HOST_EMU" not in " ".join(build.NVCC_FLAGS) and any("sm_100a" in f for f in build.NVCC_FLAGS)
+    syms = subprocess.run(["nm", "-DC", built_lib], capture_output=True, text=True).stdout
+    assert "emu::" not in syms and "launch_impl" not in syms
+    elf = subprocess.run(["cuobjdump", "-lelf", built_lib], capture_output=True, text=True)
+    if elf.returncode == 0:
+        assert "sm_100a" in elf.stdout
+    for f in ("_capi.py", "build.py", "env.py"):
+        src = open(os.path.join(ROOT, "mapdn_b200", f)).read()
+        assert "emu" not in src.replace("enumerate", "") or f == "env.py" and "tests/emu" not in src
