@@ -100,7 +100,15 @@ class DeviceTransitionBuffer:
         self.head = self.count = 0
 
     def add(self, **fields):
-        """One lock-step: every field ``[B, ...]``."""
+        """One lock-step: every field ``[B, ...]``. The width of ``value`` / ``next_value`` is the learner's business (one
+        Q per agent for most of the reference's algorithms, two for MATD3's twin critics, ``sample_size`` coalition
+        values for SQDDPG): the two arrays are re-shaped to what the first lock-step delivers."""
+        for k in ("value", "next_value"):
+            v = fields[k].reshape(self.B, self.data[k].shape[2], -1)
+            if v.shape[2] != self.data[k].shape[3]:
+                if self.count:
+                    raise ValueError(f"{k}: width changed from {self.data[k].shape[3]} to {v.shape[2]}")
+                self.data[k] = torch.zeros(self.S, self.B, v.shape[1], v.shape[2], dtype=self.data[k].dtype, device=self.device)
         for k in TRANSITION_FIELDS:
             self.data[k][self.head].copy_(fields[k].reshape(self.data[k][self.head].shape))
         self.head = (self.head + 1) % self.S

@@ -120,3 +120,50 @@ def test_reference_maddpg_learns_from_device_batches(reference_on_path):
     assert updates and all(updates) and "mean_train_value_loss" in stat and np.isfinite(stat["mean_train_value_loss"])
     ev = runner.evaluation({}, num_eval_episodes=B)
     assert abs(ev["mean_test_destroy"] - 10.0) < 1e-12 and np.isfinite(ev["mean_test_reward"])
+
+
+def _reference_trainer(alg, n_agents, obs_dim, max_steps):
+    import yaml
+    from models.model_registry import Model as REGISTRY
+    from utilities.trainer import PGTrainer
+    d = yaml.safe_load(open(os.path.join(REF, "args", "default.yaml")))
+    d.update(yaml.safe_load(open(os.path.join(REF, "args", "alg_args", alg + ".yaml")))["alg_args"])
+    d.update(agent_num=n_agents, obs_size=obs_dim, action_dim=1, cuda=False, max_steps=max_steps, action_scale=0.8,
+             action_bias=0.0, batch_size=8)
+    args = namedtuple("Args", d.keys())(**d)
+    return args, PGTrainer(args, REGISTRY[alg], env=None, logger=None)
+
+
+@pytest.mark.parametrize("alg", ["iddpg", "maddpg", "matd3", "sqddpg", "facmaddpg", "mappo", "ippo", "coma"])
+def test_reference_algorithms_run_unchanged_on_device_batches(reference_on_path, alg):
+    """Eight of the ten algorithms of the reference's registry (models/model_registry.py) collect experience through the
+    batched runner and run their own get_loss / optimiser steps on the device batches: deterministic and Gaussian
+    policies, twin critics (MATD3: value width 2), coalition sampling (SQDDPG: value width sample_size), a mixer
+    (FACMADDPG), PPO / COMA advantage code. Not covered, for reasons upstream: IAC (`self.cuda_` is never set:
+    models/iac.py:90 raises AttributeError with the reference's own env too) and MAAC (its value() returns a
+    concatenation that is not [batch, n, k]-shaped, models/maac.py:47-66)."""
+    from mapdn_b200.marl_runner import BatchedMarlRunner, DeviceTransitionBuffer, attach
+    B, n, od, T = 5, 3, 7, 6
+    args, trainer = _reference_trainer(alg, n, od, max_steps=T)
+    net = attach(trainer.behaviour_net)
+    env = FakeBatchedEnv(B, n, od, episode_limit=4)
+    buf = DeviceTransitionBuffer(32, B, n, od, act_dim=1, hid_dim=args.hid_size, device=env.device)
+    updates = []
+
+    def update(runner, stat):
+        if len(runner.buffer) >= 2 * args.batch_size:
+            batch = runner.buffer.get_batch(args.batch_size, n_windows=2)
+            w0 = [p.detach().clone() for p in trainer.behaviour_net.policy_dicts.parameters()]
+            trainer.value_transition_process(stat, batch)
+            trainer.policy_transition_process(stat, batch)
+            if args.mixer:
+                trainer.mixer_transition_process(stat, batch)
+            updates.append(any(not torch.equal(a, b) for a, b in zip(w0, trainer.behaviour_net.policy_dicts.parameters())))
+    runner = BatchedMarlRunner(env, net, buf, update_fn=update)
+    stat = runner.train_process({})
+    assert runner.steps == T * B and updates and all(updates)
+    assert np.isfinite(stat["mean_train_value_loss"]) and np.isfinite(stat["mean_train_policy_loss"])
+    a = torch.stack(env.actions_seen)
+    assert float(a.abs().max()) <= 0.8 + 1e-12                       # translate_action keeps the env's action range
+    ev = runner.evaluation({}, num_eval_episodes=B)
+    assert np.isfinite(ev["mean_test_reward"])
