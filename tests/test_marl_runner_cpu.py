@@ -167,3 +167,99 @@ def test_reference_algorithms_run_unchanged_on_device_batches(reference_on_path,
     assert float(a.abs().max()) <= 0.8 + 1e-12                       # translate_action keeps the env's action range
     ev = runner.evaluation({}, num_eval_episodes=B)
     assert np.isfinite(ev["mean_test_reward"])
+
+
+class OracleBatchedEnv:
+    """CPU stand-in with the surface of BatchedVoltageControl the runner touches, backed by the oracle restatement of the
+    env (one VoltageControlOracle per env id) - what the CUDA engine is held to by the parity tests."""
+
+    def __init__(self, net, prof, env_args, batch):
+        from oracle.voltage_control_ref import INFO_KEYS, VoltageControlOracle
+        self.keys = INFO_KEYS
+        self.envs = [VoltageControlOracle(net, prof, env_args, env_id=i) for i in range(batch)]
+        self.batch, self.n_agents, self.n_actions = batch, net.n_sgen, 1
+        self.device = torch.device("cpu")
+        self.obs = None
+
+    def _snap(self):
+        self.obs = torch.tensor(np.array([np.array(e.get_obs()) for e in self.envs]))
+        self.obs_size = self.obs.shape[-1]
+
+    def reset(self, mask=None, want_state=True, **kw):
+        for i, e in enumerate(self.envs):
+            if mask is None or bool(mask[i]):
+                e.reset()
+        self._snap()
+        return self.obs, None
+
+    def step(self, a):
+        out = [e.step(a[i].numpy()) for i, e in enumerate(self.envs)]
+        self._snap()
+        return (torch.tensor([o[0] for o in out]), torch.tensor([int(o[1]) for o in out], dtype=torch.uint8),
+                torch.tensor([[o[2][k] for k in self.keys] for o in out]))
+
+
+@pytest.mark.parametrize("alg", ["maddpg", "mappo"])
+def test_runner_collects_what_the_reference_train_process_collects(reference_on_path, alg, tmp_path):
+    """End to end against the reference's OWN loop: `Model.train_process` (models/model.py:197-263) drives the reference's
+    own env (oracle/ref_harness.py) with the reference's own learner; the batched runner drives the oracle-backed stand-in
+    with a copy of the same learner and the same torch seed. Every field of every transition (state, action, value,
+    next_value, reward, next_state, done, last_step, last_hid, hid) and the mean_train_* statistics agree."""
+    import copy
+    from mapdn_b200 import cases
+    from mapdn_b200.marl_runner import BatchedMarlRunner, DeviceTransitionBuffer, attach
+    from oracle import ref_harness as H
+    net, prof = cases.make_case("case33"), cases.make_profiles("case33", n_days=4)
+    env_args = dict(voltage_barrier_type="bowl", action_scale=0.8, action_bias=0.0, seed=21)
+    H.write_reference_data(str(tmp_path), net, prof)
+    ref = H.ReferenceRun(str(tmp_path), net, env_args, env_id=0)             # episode 1 = the constructor's reset
+    T = 5
+    args, trainer = _reference_trainer(alg, net.n_sgen, ref.env.get_obs_size(), max_steps=T)
+    args = args._replace(replay_warmup=10 ** 9)                                # collection only: no update inside the loop
+    trainer.args = args
+    trainer.behaviour_net.args = args
+    model_copy = copy.deepcopy(trainer.behaviour_net)
+
+    class Hooked:                                                              # tells the harness which draws come next
+        def __init__(self, run):
+            self._r = run
+
+        def reset(self):
+            self._r.draws.begin_reset()
+            return self._r.env.reset()
+
+        def step(self, a):
+            self._r.draws.begin_step()
+            return self._r.env.step(a)
+
+        def __getattr__(self, k):
+            return getattr(self._r.env, k)
+
+    trainer.env = Hooked(ref)
+    torch.manual_seed(5)
+    stat_ref = {}
+    with ref._ctx():
+        trainer.behaviour_net.train_process(stat_ref, trainer)
+    trans = trainer.replay_buffer.buffer
+    assert len(trans) == T and trainer.steps == T
+
+    env = OracleBatchedEnv(net, prof, env_args, batch=1)
+    env.reset()                                                                # episode 1, like the reference's constructor
+    buf = DeviceTransitionBuffer(T, 1, net.n_sgen, ref.env.get_obs_size(), act_dim=1, hid_dim=args.hid_size, device=env.device)
+    runner = BatchedMarlRunner(env, attach(model_copy), buf)
+    torch.manual_seed(5)
+    stat = runner.train_process({})
+    st, ac, lp, v, nv, rw, ns, dn, ls, av, lh, h = buf.latest(T).unpacked()
+    tol = 2e-5                                                                 # the learner computes in fp32
+    for t, tr in enumerate(trans):
+        assert np.abs(np.array(tr.state) - st[t].numpy()).max() < tol and np.abs(np.array(tr.next_state) - ns[t].numpy()).max() < tol
+        assert np.abs(tr.action.reshape(-1) - ac[t].numpy().reshape(-1)).max() < tol
+        assert np.abs(tr.value.reshape(-1) - v[t].numpy().reshape(-1)).max() < 1e-4
+        assert np.abs(tr.next_value.reshape(-1) - nv[t].numpy().reshape(-1)).max() < 1e-4
+        assert np.abs(tr.reward - rw[t].numpy()).max() < tol
+        assert float(tr.done) == float(dn[t]) and float(tr.last_step) == float(ls[t])
+        assert np.abs(tr.last_hid.reshape(-1) - lh[t].numpy().reshape(-1)).max() < tol
+        assert np.abs(tr.hid.reshape(-1) - h[t].numpy().reshape(-1)).max() < tol
+    for k, v_ref in stat_ref.items():
+        if k.startswith("mean_train_"):
+            assert abs(stat[k] - v_ref) < 1e-5, k
