@@ -263,3 +263,13 @@ def test_runner_collects_what_the_reference_train_process_collects(reference_on_
     for k, v_ref in stat_ref.items():
         if k.startswith("mean_train_"):
             assert abs(stat[k] - v_ref) < 1e-5, k
+    # Model.evaluation (models/model.py:265-302): greedy episodes, per-episode means averaged over the episodes
+    args = args._replace(num_eval_episodes=2)
+    trainer.args = trainer.behaviour_net.args = model_copy.args = args
+    ev_ref = {}
+    with ref._ctx():
+        trainer.behaviour_net.evaluation(ev_ref, trainer)
+    ev = runner.evaluation({}, num_eval_episodes=2)
+    assert len(ev_ref) == 12
+    for k, v_ref in ev_ref.items():
+        assert abs(ev[k] - v_ref) < 1e-5, k
