@@ -49,3 +49,41 @@ def test_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_reference_fixture_leg_of_the_parity_record():
+    """bench.py's `parity.reference_fixture` leg replays a reference-executed fixture through the engine; here through an
+    oracle-backed CPU stand-in of the engine's surface, to check the replay logic itself."""
+    import numpy as np
+    import torch
+    from oracle.voltage_control_ref import INFO_KEYS, VoltageControlOracle
+    bench = _bench()
+
+    class Standin:
+        def __init__(self, net, prof, args, B):
+            self.o = [VoltageControlOracle(net, prof, args, env_id=i) for i in range(B)]
+            self.device, self.obs = torch.device("cpu"), None
+
+        def _snap(self):
+            self.obs = torch.tensor(np.array([np.array(o.get_obs()) for o in self.o]))
+
+        def reset(self, start=None, add_noise=True):
+            for i, o in enumerate(self.o):
+                o.reset(start=None if start is None else tuple(start[i].tolist()), add_noise=add_noise)
+            self._snap()
+
+        def step(self, a, add_noise=True):
+            out = [o.step(a[i].numpy(), add_noise=add_noise) for i, o in enumerate(self.o)]
+            self._snap()
+            return (torch.tensor([x[0] for x in out]), torch.tensor([int(x[1]) for x in out], dtype=torch.uint8),
+                    torch.tensor([[x[2][k] for k in INFO_KEYS] for x in out]))
+
+        def get_state(self):
+            return torch.tensor(np.array([o.get_state() for o in self.o]))
+
+        def close(self):
+            pass
+    for name in ("case33_bowl", "case33_divergence"):
+        rec = bench.reference_fixture_check(0, name=name, make_env=Standin)
+        assert rec["n_steps"] >= 6 and rec["max_abs_dreward"] < 1e-11 and rec["max_abs_dinfo"] < 1e-11
+        assert rec["max_abs_dobs"] < 1e-11 and rec["max_abs_dstate"] < 1e-9
