@@ -313,7 +313,7 @@ __device__ __forceinline__ bool nr_solve(const Params& p, const Hot& h, const Sl
   // The FIRST Newton iteration is static up to its right-hand side: at the flat start S_calc and the Jacobian are the same
   // for every env and every step, so mapdn_create factorises J(V0) once (p.first_tab, six double2 per node: S_calc,
   // M = D'^-1 J[i,parent] (two rows), D'^-1 (two rows), J[parent,i]) and this pass seeds the records with it: the mismatch
-  // is S_calc - S_spec, the forward sweep only eliminates the right-hand side (first_sweep below: D'^-1 from UP / DN,
+  // is S_calc - S_spec, the forward sweep only eliminates the right-hand side (sweep1 below: D'^-1 from UP / DN,
   // J[parent,i] from T), the back sweep finds M where a regular elimination would have left it (D01 / D23). pandapower
   // computes the same factors numerically in every runpp; the iterates agree to rounding.
   double nrm = 0.0;
