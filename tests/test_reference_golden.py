@@ -236,3 +236,16 @@ def test_drop_in_class_reproduces_the_reference_trajectories(name):
     info_env = env.get_env_info()
     assert info_env["n_agents"] == ng and info_env["obs_shape"] == g["obs"].shape[-1] and info_env["state_shape"] == g["state"].shape[-1]
     env.close()
+
+
+@pytest.mark.skipif(not _reference_here(), reason="/root/reference is not available on this machine")
+def test_reference_decentralised_mode_is_broken_upstream(tmp_path):
+    """`mode="decentralised"` cannot even construct the reference env: `get_obs` indexes `clusters["sgen0"]`
+    (voltage_control_env.py:239), a key that only the distributed branch of `_get_clusters_info` creates. The product
+    therefore raises NotImplementedError for that mode instead of inventing semantics."""
+    from mapdn_b200 import cases
+    from oracle import ref_harness as H
+    net, prof = cases.make_case("case33"), cases.make_profiles("case33", n_days=3)
+    H.write_reference_data(str(tmp_path), net, prof)
+    with pytest.raises(KeyError, match="sgen0"):
+        H.ReferenceRun(str(tmp_path), net, dict(mode="decentralised", seed=0), env_id=0)
