@@ -519,7 +519,7 @@ def reference_fixture_check(local, name="case33_bowl", make_env=None):
     else:
         env = make_env(net, prof, sc["args"], B)
     d_obs = d_state = d_reward = d_info = 0.0
-    t = n_steps = 0
+    t = n_steps = n_reset = 0
     for k_op, op in enumerate(ops):
         if op[0] == "step":
             a = np.zeros((B, net.n_sgen))
@@ -535,13 +535,14 @@ def reference_fixture_check(local, name="case33_bowl", make_env=None):
             if live.size == 0:
                 continue
         else:
-            if op[0] == "manual":
+            if op[0] in ("manual", "reset_keep"):
                 start = np.zeros((B, 3), np.int32)
                 for k, e in enumerate(ids):
-                    start[e] = S.manual_of(sc, op, k)
-                env.reset(torch.tensor(start, device=env.device), add_noise=False)
+                    start[e] = S.manual_of(sc, op, k) if op[0] == "manual" else g["start"][n_reset - 1, k]
+                env.reset(torch.tensor(start, device=env.device), add_noise=(op[0] == "reset_keep"))
             else:
                 env.reset()
+            n_reset += 1
             live, sel = np.arange(len(ids)), list(ids)
         obs = env.obs[sel].cpu().numpy()
         d_obs = max(d_obs, float(np.abs(obs - g["obs"][k_op, live][..., -obs.shape[-1]:]).max()))

@@ -409,6 +409,13 @@ class ReferenceRun:
             obs, state = self.env.reset()
         return np.array(obs), np.array(state)
 
+    def reset_keep_time(self):
+        """``reset(reset_time=False)``: a new episode at the previous start (noise and reset action re-drawn, :109-122)."""
+        self.draws.begin_reset()
+        with self._ctx():
+            obs, state = self.env.reset(reset_time=False)
+        return np.array(obs), np.array(state)
+
     def manual_reset(self, day, hour, interval):
         self.draws.begin_reset()
         with self._ctx():

@@ -8,6 +8,7 @@ A scenario = network + profile store + env args + the global env ids whose RNG s
     ("init",)                      the reset that the reference's ``__init__`` performs (:85) = first ``reset()`` here
     ("reset",)                     ``reset()``: sampled start, noise on, random reset action (:96-133)
     ("manual", day, hour, intv)    ``manual_reset(day, hour, interval)``: noise off (:135-176)
+    ("reset_keep",)                ``reset(reset_time=False)``: the previous start again, noise / reset action re-drawn
     ("step", add_noise)            ``step(actions, add_noise)`` followed by ``get_obs()`` / ``get_state()`` (:178-316)
 
 Actions are drawn from ``np.random.default_rng`` seeded per scenario, uniformly in the env's action range.
@@ -113,6 +114,8 @@ _add("case33_state_space", lambda: _case("case33"),
 # stacked rows, the batched engine / the oracle restatement are compared on the newest frame
 _add("case33_history", lambda: _case("case33"), dict(voltage_barrier_type="l1", action_scale=0.8, seed=12, history=3), (0,),
      [("init",)] + [("step", True)] * 3 + [("reset",), ("step", True)])
+_add("case33_reset_keep", lambda: _case("case33"), dict(voltage_barrier_type="l2", action_scale=0.8, seed=14), (0, 2),
+     [("init",), ("step", True), ("reset_keep",), ("step", True), ("step", True)])
 # manual starts at rows 55..58 (day 0, hour 2, interval 15 + k): the overload begins at row 60
 _add("case33_divergence", _overload_case, dict(voltage_barrier_type="l1", action_scale=0.8, seed=7), (0, 1, 2, 3),
      [("init",), ("manual", 0, 2, 15)] + [("step", False)] * 7, per_env_manual=lambda k: (0, 2, 15 + (k % 4)))

@@ -58,6 +58,8 @@ def record(sc, view_rows=True):
                     o, s = r.reset()
                 elif op[0] == "manual":
                     o, s = r.manual_reset(*S.manual_of(sc, op, k))
+                elif op[0] == "reset_keep":
+                    o, s = r.reset_keep_time()
                 elif dead[k]:
                     alive[t, k] = 0
                     o, s = obs[-1][k], state[-1][k]

@@ -94,7 +94,8 @@ def test_emulated_trajectory_matches_oracle(name, barrier, batch, lanes):
     env.close()
 
 
-@pytest.mark.parametrize("name", ["case33_bowl", "general_line_weight", "case33_state_space", "case33_divergence", "case141_l1"])
+@pytest.mark.parametrize("name", ["case33_bowl", "general_line_weight", "case33_state_space", "case33_divergence", "case141_l1",
+                                  "case33_reset_keep"])
 def test_emulated_kernel_reproduces_the_reference_executed_fixtures(name):
     """The kernel source, on the CPU, against trajectories the reference's own env code produced
     (tests/golden/ref_env_*.npz, see tests/test_reference_golden.py)."""
@@ -105,7 +106,7 @@ def test_emulated_kernel_reproduces_the_reference_executed_fixtures(name):
     ids = sc["env_ids"]
     B = max(ids) + 1
     env = EmuEnv(net, prof, sc["args"], batch=B)
-    t = 0
+    t = n_reset = 0
     for k_op, op in enumerate(ops):
         if op[0] == "step":
             a = np.zeros((B, net.n_sgen))
@@ -120,13 +121,14 @@ def test_emulated_kernel_reproduces_the_reference_executed_fixtures(name):
             if live.size == 0:
                 continue
         else:
-            if op[0] == "manual":
+            if op[0] in ("manual", "reset_keep"):
                 start = np.zeros((B, 3), np.int32)
                 for k, e in enumerate(ids):
-                    start[e] = S.manual_of(sc, op, k)
-                env.reset(start, add_noise=False)
+                    start[e] = S.manual_of(sc, op, k) if op[0] == "manual" else g["start"][n_reset - 1, k]
+                env.reset(start, add_noise=(op[0] == "reset_keep"))
             else:
                 env.reset()
+            n_reset += 1
             live, sel = np.arange(len(ids)), ids
         assert np.abs(env.obs[sel] - g["obs"][k_op, live][..., -env.dims["obs_dim"]:]).max() < TOL
         assert np.abs(env.get_state()[sel] - g["state"][k_op, live]).max() < 1e-8

@@ -64,6 +64,8 @@ def test_oracle_reproduces_the_reference_trajectories(name):
             else:
                 if op[0] == "manual":
                     obs, st = o.reset(start=S.manual_of(sc, op, k), add_noise=False)
+                elif op[0] == "reset_keep":                      # reset(reset_time=False): the previous start, noise on
+                    obs, st = o.reset(start=tuple(int(x) for x in g["start"][n_reset - 1, k]), add_noise=True)
                 else:
                     obs, st = o.reset()
                 day, hour, interval = g["start"][n_reset, k]
@@ -81,7 +83,8 @@ def _reference_here():
 
 
 @pytest.mark.skipif(not _reference_here(), reason="/root/reference is not available on this machine")
-@pytest.mark.parametrize("name", ["case33_bowl", "general_line_weight", "case33_divergence", "case33_state_space", "case33_history"])
+@pytest.mark.parametrize("name", ["case33_bowl", "general_line_weight", "case33_divergence", "case33_state_space", "case33_history",
+                                  "case33_reset_keep"])
 def test_reference_rerun_reproduces_the_committed_fixture(name):
     import importlib.util
     spec = importlib.util.spec_from_file_location("make_reference_golden", os.path.join(ROOT, "scripts", "make_reference_golden.py"))
@@ -171,11 +174,11 @@ def test_cuda_path_reproduces_the_reference_trajectories(name):
             if live.size == 0:          # every env of the scenario has terminated (the reference's caller would reset)
                 continue
         else:
-            if op[0] == "manual":
+            if op[0] in ("manual", "reset_keep"):
                 start = np.zeros((B, 3), np.int32)
                 for k, e in enumerate(ids):
-                    start[e] = S.manual_of(sc, op, k)
-                env.reset(torch.tensor(start, device=env.device), add_noise=False)
+                    start[e] = S.manual_of(sc, op, k) if op[0] == "manual" else g["start"][n_reset - 1, k]
+                env.reset(torch.tensor(start, device=env.device), add_noise=(op[0] == "reset_keep"))
             else:
                 env.reset()
             st = env.get_state()
@@ -217,6 +220,8 @@ def test_drop_in_class_reproduces_the_reference_trajectories(name):
             obs, state = env.get_obs(), env.get_state()
         elif op[0] == "reset":
             obs, state = env.reset()
+        elif op[0] == "reset_keep":
+            obs, state = env.reset(reset_time=False)
         else:
             obs, state = env.manual_reset(*S.manual_of(sc, op, 0))
         if op[0] != "step":
