@@ -291,3 +291,36 @@ def test_emulated_host_paths_deliver_the_same_transition(scenario, batch):
             assert not np.any(o[:, sum(n for _, n in slices):])
     for e in envs:
         e.close()
+
+
+def test_plain_c_caller_through_the_emulated_library():
+    """examples/c_abi_demo.c (strict C99, host buffers, no CUDA header) linked against the EMULATED library: the whole
+    boundary - C caller -> extern "C" entry points -> host code -> kernel source - runs on the CPU and prints what the
+    NumPy binding of the same library computes for the same feeder. (Against the real library the demo fails loudly
+    without a GPU: tests/test_c_abi_demo.py.)"""
+    import shutil
+    import subprocess
+    from emu_env import build as build_emu
+    from test_c_abi_demo import SRC, _demo_inputs
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    lib = build_emu()
+    exe = os.path.join(os.path.dirname(lib), "c_abi_demo_emu")
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-O2", "-I", os.path.join(ROOT, "include"), SRC,
+                        "-o", exe, lib, "-Wl,-rpath," + os.path.dirname(lib), "-lm"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    got = [ln.split() for ln in lines if ln.startswith("step ")]
+    assert lines[0].startswith("dims n_agents 2 obs_dim ") and len(got) == 10
+    net, prof = _demo_inputs()
+    env = EmuEnv(net, prof, dict(voltage_barrier_type="bowl", seed=2024, action_scale=0.8), batch=8)
+    env.reset()
+    for k in range(10):
+        a = np.array([[-0.8 + 1.6 * ((e * 7 + g * 3 + k) % 11) / 10.0 for g in range(2)] for e in range(8)])
+        rew, term, _ = env.step(a)
+        rs, os_ = float(got[k][2]), float(got[k][3])
+        assert abs(rs - float(rew.sum())) < 1e-12 * max(1.0, abs(rs)) and abs(os_ - float(env.obs.sum())) < 1e-12 * max(1.0, abs(os_))
+        assert int(got[k][4]) == int(term.sum())
+    env.close()
